@@ -1,0 +1,243 @@
+/*
+ * pkv.h — C ABI of the B200-native vector-similarity operator for Panoptikon.
+ *
+ * This is the drop-in boundary for ONE path of reasv/panoptikon: the PQL vector
+ * filters' brute-force scan, which the reference executes row-at-a-time inside
+ * SQLite through sqlite-vec's vec_distance_L2 / vec_distance_cosine / vec_int8
+ * plus a small Rust int8 codec.  Paths below are relative to
+ * /root/reference/panoptikon/src unless they start with docs/.
+ *
+ * Conventions
+ *   - plain C types only; every function returns a pkv_status (0 = ok) unless
+ *     stated otherwise; the message for the calling thread's last failure is
+ *     pkv_last_error().  No C++ exception or abort crosses this boundary.
+ *   - inputs are borrowed for the duration of the call (the Rust side hands
+ *     `&[u8]` / `Vec<u8>` blobs: pql/embedding_utils.rs:15-21,
+ *     builder/filters/embedding_types.rs:71-76); outputs are caller-allocated.
+ *   - blobs use the reference's storage layout: one vector = D little-endian
+ *     f32 (`embeddings.embedding`, migrations/index/20250117193000_init.sql:29-33)
+ *     or D int8 codes (`embedding_quants.quant`,
+ *     migrations/index/20260730150000_embedding_quants_rowid.sql:32-48), no header.
+ *   - all entry points are re-entrant; searches may run concurrently from many
+ *     threads (the reference's read pool is 16 threads: db/connection.rs:235),
+ *     append/seal take the index exclusively.
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     PKV_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Ordering contract (the reference leaves ties to SQLite's plan order,
+ * builder.rs:1188-1205; its own golden harness appends a stable key,
+ * pql/quant_ab.rs:32-42): ascending f32 distance, ties by ascending row id
+ * position (insertion order), NaN distances (SQL NULL, "NULLS LAST") last.
+ */
+#ifndef PKV_H
+#define PKV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PKV_ABI_VERSION 1
+
+typedef enum {
+    PKV_OK = 0,
+    PKV_ERR_INVALID = 1,      /* bad argument (maps to PqlError::invalid -> HTTP 400, api/search.rs:1664) */
+    PKV_ERR_DIM_MISMATCH = 2, /* pql/preprocess.rs:372-381 */
+    PKV_ERR_NOT_READY = 3,    /* quant pair not ready (db/vector_quants.rs:1829-1850) / index not sealed */
+    PKV_ERR_CUDA = 4,         /* device failure (maps to ApiError::internal, db/pql.rs:18-21) */
+    PKV_ERR_OOM = 5,
+    PKV_ERR_UNSUPPORTED = 6
+} pkv_status;
+
+/* element type of the stored rows */
+typedef enum {
+    PKV_F32 = 0, /* embeddings.embedding: D x LE f32 */
+    PKV_I8 = 1,  /* embedding_quants.quant: D x int8 (vec_int8 blobs, docs/vector-int8-quant.md:11-49) */
+    PKV_F16 = 2  /* framework extension (BASELINE config 4); the reference always stores f32 */
+} pkv_dtype;
+
+/* distance function: builder/filters/embedding_types.rs:20-42 (serde names "L2"/"COSINE").
+ * PKV_DOT (distance = -dot) is the benchmark-only metric of BASELINE config 3. */
+typedef enum { PKV_L2 = 0, PKV_COSINE = 1, PKV_DOT = 2 } pkv_metric;
+
+typedef struct pkv_index pkv_index; /* opaque; owned by the library */
+
+typedef struct {
+    int32_t abi_version;
+    int32_t device;
+    int32_t dim;
+    int32_t dtype;    /* pkv_dtype */
+    int32_t sealed;   /* 1 after pkv_index_seal: searchable */
+    int32_t has_scale;
+    float scale;      /* int8 scale (valid when has_scale) */
+    int64_t rows;
+    int64_t capacity_rows;
+    int64_t device_bytes; /* HBM held by the corpus + per-row side arrays */
+    int64_t row_base;
+} pkv_index_info;
+
+/* -- library ---------------------------------------------------------------- */
+int pkv_abi_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *pkv_last_error(void);
+/* Number of usable CUDA devices; 0 (and PKV_ERR_CUDA) when there is none. */
+int pkv_device_count(int *count);
+
+/* -- int8 codec: db/vector_quants.rs:1446-1503 ------------------------------- */
+/* scale_from_absmax (:1465-1471): absmax/127, or 1.0 when absmax is not a positive finite value. */
+float pkv_scale_from_absmax(float absmax);
+/* scale_artifact (:1449-1451): the 4-byte little-endian f32 payload. */
+void pkv_scale_artifact(float scale, uint8_t out[4]);
+/* artifact_scale (:1456-1460): PKV_OK and *scale, or PKV_ERR_INVALID for anything that
+ * is not exactly 4 bytes holding a positive finite f32. */
+int pkv_artifact_scale(const uint8_t *artifact, size_t len, float *scale);
+/* blob_absmax over `n` LE f32 components in HOST memory, reduced on the GPU
+ * (:1474-1483; NaN never replaces the running max). */
+int pkv_blob_absmax(int device, const float *values, int64_t n, float *absmax);
+/* quantize_int8 / compute_query_quant (:1489-1503) for `n` components in HOST memory,
+ * computed on the GPU, bit-exact with the Rust codec:
+ * clamp(round_ties_even(x / scale), -128, 127) as i8, NaN -> 0. */
+int pkv_quantize_int8(int device, const float *values, int64_t n, float scale, int8_t *codes);
+/* Same two operations on DEVICE pointers (bulk corpus build, replaces the 5000-row
+ * backfill chunks of db/vector_quants.rs:1085-1163).  stream is a cudaStream_t or NULL. */
+int pkv_blob_absmax_device(int device, const float *d_values, int64_t n, float *absmax, void *stream);
+int pkv_quantize_int8_device(int device, const float *d_values, int64_t n, float scale, int8_t *d_codes,
+                             void *stream);
+
+/* -- index lifecycle --------------------------------------------------------- */
+/* One index = one (setter space, payload) pair resident in one GPU's HBM: the
+ * `embeddings` rows of a setter (PKV_F32) or its `embedding_quants` rows for one
+ * (profile_id, artifact_rev) (PKV_I8). */
+int pkv_index_create(int device, int dim, int dtype, pkv_index **out);
+int pkv_index_destroy(pkv_index *h);
+int pkv_index_reserve(pkv_index *h, int64_t rows);
+/* Appends `n` rows given as concatenated blobs exactly as SQLite stores them
+ * (n * dim * elem_size bytes, HOST memory).  row_ids: the n `item_data.id` values
+ * (embeddings.id), or NULL for row_base + position.  Copies; never retains pointers. */
+int pkv_index_append(pkv_index *h, const void *rows, const int64_t *row_ids, int64_t n);
+/* Same with DEVICE pointers (rows and row_ids already in this GPU's HBM). */
+int pkv_index_append_device(pkv_index *h, const void *d_rows, const int64_t *d_row_ids, int64_t n);
+/* int8 only: the frozen scale artifact of the pair (vector_quant_coverage.artifact,
+ * migrations/index/20260720130000_vector_quants.sql:12-29).  Rejected like artifact_scale. */
+int pkv_index_set_scale(pkv_index *h, const uint8_t *artifact, size_t len);
+/* First global row number of this shard when the corpus is row-sharded over GPUs;
+ * only affects ids reported for rows appended with row_ids == NULL. */
+int pkv_index_set_row_base(pkv_index *h, int64_t row_base);
+/* Makes appended rows searchable (computes the per-row side arrays). Idempotent;
+ * appending after a seal un-seals the new rows until the next seal. */
+int pkv_index_seal(pkv_index *h);
+int pkv_index_get_info(const pkv_index *h, pkv_index_info *info);
+
+/* -- search: replaces the materialised distance CTE of builder/filters/exact.rs:106-165
+ *    (`dist_{cte}(.., d)` = vec_distance_*(stored, ?) over every candidate row),
+ *    truncated to retrieval depth k — the reserved `index`/`k` seam of
+ *    builder/filters/embedding_types.rs:44-66 / docs/vector-int8-quant.md:86-88. */
+typedef struct {
+    int32_t metric;       /* pkv_metric */
+    int32_t k;            /* retrieval depth, 1..PKV_MAX_K */
+    int32_t query_dtype;  /* PKV_F32, or PKV_I8 codes (QuantResolved.query_quant) for an int8
+                             index, or PKV_F16 for an f16 index.  f32 queries against an int8
+                             index are quantised on the GPU with the index scale
+                             (compute_query_quant, db/vector_quants.rs:1501-1503). */
+    int32_t reserved;
+    /* Optional membership filter ("∩ context", image_embeddings.rs:140-199): LSB-first
+     * u64 words, bit r set <=> stored row r may be returned.  NULL = all rows.
+     * bitmap_stride_words = 0: one bitmap for every query; else words per query. */
+    const uint64_t *bitmap;
+    int64_t bitmap_stride_words;
+} pkv_search_params;
+
+#define PKV_MAX_K 4096 /* the server clamps LIMIT to 4096 (api/search.rs:51) */
+
+/* HOST buffers.  queries: nq blobs of dim components.  out_ids / out_dist: nq*k,
+ * best first; out_counts: nq (number of valid entries; the tail is id -1 / NaN). */
+int pkv_search(pkv_index *h, const void *queries, int nq, const pkv_search_params *params,
+               int64_t *out_ids, float *out_dist, int32_t *out_counts);
+/* DEVICE buffers (queries, bitmap and outputs in this GPU's HBM), work enqueued on
+ * `stream` (cudaStream_t or NULL); returns after the results are complete. */
+int pkv_search_device(pkv_index *h, const void *d_queries, int nq, const pkv_search_params *params,
+                      int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts, void *stream);
+
+/* Merge `parts` per-shard result lists (each nq*k, laid out [part][nq][k], as gathered
+ * by one NCCL all-gather) into the global top-k under the same total order.
+ * DEVICE buffers. */
+int pkv_merge_topk_device(int device, const int64_t *d_ids, const float *d_dist, int parts, int nq, int k,
+                          int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts, void *stream);
+
+/* Per-item aggregation of row distances (builder/filters/exact.rs:67-80):
+ * agg 0 MIN / 1 MAX / 2 AVG of d grouped by item, or SUM(d*w)/SUM(w) when d_weights
+ * is non-NULL.  item ids are dense 0..n_items-1; NaN rows are skipped (SQL NULL);
+ * out[i] = NaN for items without rows.  DEVICE buffers. */
+int pkv_aggregate_device(int device, const float *d_dist, const int64_t *d_item_of_row, const float *d_weights,
+                         int64_t n, int64_t n_items, int agg, double *d_out, void *stream);
+
+/* -- counters for the bench (cumulative since create) ------------------------- */
+typedef struct {
+    int64_t searches;
+    int64_t queries;
+    int64_t kernel_launches;    /* our own kernels launched by searches */
+    int64_t scan_launches;      /* the dominant (scan) kernels among them */
+    int64_t fallback_queries;   /* queries re-run on the small-chunk schedule after a candidate overflow */
+    double last_scan_ms;        /* CUDA-event time of the scan kernels of the last search on this thread */
+    double last_total_ms;       /* CUDA-event time of the last search's device work */
+    int32_t last_scan_kind;     /* which scan kernel family ran: 1 simt-f32, 2 simt-i8, 3 tc-i8, 4 tc-tf32, 5 simt-f16, 6 tc-f16 */
+    int32_t reserved;
+} pkv_counters;
+int pkv_index_counters(pkv_index *h, pkv_counters *out);
+/* Tuning knobs for tests and the bench: name = "force_simt" (0/1), "candidate_capacity",
+ * "first_chunk_rows", "chunk_growth_x100", "time_kernels" (0/1). */
+int pkv_index_set_option(pkv_index *h, const char *name, int64_t value);
+
+/* -- PQL operator policy: pql/preprocess.rs:314-465, builder/filters/embedding_types.rs --- */
+typedef enum { PKV_INDEX_AUTO = 0, PKV_INDEX_EXACT = 1, PKV_INDEX_QUANT = 2, PKV_INDEX_ANN = 3 } pkv_index_mode;
+typedef enum { PKV_AGG_MIN = 0, PKV_AGG_MAX = 1, PKV_AGG_AVG = 2 } pkv_distance_aggregation;
+#define PKV_DEFAULT_K 10000 /* default_k(), embedding_types.rs:64-66 */
+
+/* serde names -> enums; PKV_ERR_INVALID for unknown names.
+ * IndexMode: "auto"/"exact"/"quant"/"ann"; DistanceFunction: "L2"/"COSINE"
+ * (from_override, embedding_types.rs:28-36, is case-insensitive); aggregation "MIN"/"MAX"/"AVG". */
+int pkv_parse_index_mode(const char *name, int *mode);
+int pkv_parse_distance_function(const char *name, int case_insensitive, int *metric);
+int pkv_parse_distance_aggregation(const char *name, int *agg);
+/* validate_quant_args (preprocess.rs:436-446) */
+int pkv_validate_quant_args(int index_mode, int64_t k);
+/* quant_requested (preprocess.rs:413-421): 1/0 */
+int pkv_quant_requested(int index_mode, const char *variant_or_null);
+/* strict = index == quant || normalize_variant(variant).is_some() (preprocess.rs:331-332,425-431) */
+int pkv_quant_strict(int index_mode, const char *variant_or_null);
+
+/* A ReadyPair (db/vector_quants.rs:1784-1788) as the operator needs it. */
+typedef struct {
+    int64_t profile_id;
+    float scale;
+    int64_t dim;
+} pkv_ready_pair;
+
+/* A searchable "space": the exact f32 index of a setter and, optionally, the int8 index
+ * of its ready quant profile.  Mirrors what resolve_vector_quant + the filter compilers
+ * decide per request (preprocess.rs:314-393; image_embeddings.rs:321-362):
+ *   exact            -> f32 index
+ *   auto             -> quant index of the default profile when a ready pair exists and the
+ *                       query dimension matches, else exact (silent fallback)
+ *   quant / variant  -> quant index or an error (never a silent fallback)
+ *   ann              -> rejected
+ * Neither index is owned by the space. */
+typedef struct pkv_space pkv_space;
+int pkv_space_create(const char *model, pkv_index *exact_f32, pkv_space **out);
+int pkv_space_destroy(pkv_space *s);
+/* Registers (or, with quant == NULL, withdraws) the ready pair of profile `profile_name`;
+ * is_default marks it as the configured default profile. */
+int pkv_space_set_quant(pkv_space *s, const char *profile_name, int is_default, const pkv_ready_pair *pair,
+                        pkv_index *quant_i8);
+/* One vector filter evaluation. query: nq f32 blobs of query_dim components (HOST).
+ * *used_profile_id = the profile searched, or -1 when the exact index was used. */
+int pkv_space_search(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
+                     const char *variant_or_null, int64_t k_arg, int depth, int64_t *out_ids, float *out_dist,
+                     int32_t *out_counts, int64_t *used_profile_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PKV_H */

@@ -281,5 +281,7 @@ def synthetic(n: int, d: int, seed: int = CORPUS_SEED, normalise: bool = True) -
     (mirrors tools/pql-equivalence/run_suite.py:532-542)."""
     x = np.random.default_rng(seed).standard_normal((n, d), dtype=np.float32)
     if normalise:
-        x /= np.linalg.norm(x.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+        for b in range(0, n, 65536):  # chunked: keeps the f64 temporary small
+            blk = x[b:b + 65536]
+            blk /= np.linalg.norm(blk.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
     return x

@@ -1,0 +1,724 @@
+// pkv_api.cu — the extern "C" boundary (include/pkv.h): index lifecycle, the chunked
+// scan/select search driver, codec entry points.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "pkv_internal.cuh"
+
+namespace pkv {
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+static int use_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(PKV_ERR_CUDA, "no usable CUDA device (%s); libpkv has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(PKV_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+    PKV_CUDA(cudaSetDevice(device));
+    return PKV_OK;
+}
+
+static int elem_size(int dtype) { return dtype == PKV_F32 ? 4 : (dtype == PKV_I8 ? 1 : 2); }
+static int pad_dim(int dim, int dtype) {
+    const int q = 128 / elem_size(dtype);  // components per 128-byte line
+    return (dim + q - 1) / q * q;
+}
+
+Workspace::~Workspace() {
+    cudaSetDevice(device);
+    cudaFree(d_qraw);
+    cudaFree(d_q);
+    cudaFree(d_q_mag_f);
+    cudaFree(d_q_mag_i);
+    cudaFree(d_cand);
+    cudaFree(d_cnt);
+    cudaFree(d_thr_key);
+    cudaFree(d_thr_f);
+    cudaFree(d_status);
+    if (h_status) cudaFreeHost(h_status);
+    cudaFree(d_out_ids);
+    cudaFree(d_out_dist);
+    cudaFree(d_out_counts);
+    cudaFree(d_bitmap);
+    for (auto &e : ev)
+        if (e) cudaEventDestroy(e);
+    if (owns_stream && stream) cudaStreamDestroy(stream);
+}
+
+static constexpr int SUB_BATCH = 1024;  // queries per internal pass (bounds the workspace)
+
+static int candidate_capacity(const Index &ix, int k) {
+    int64_t cap = 4096;
+    while (cap < 4 * (int64_t)k) cap <<= 1;
+    if (ix.opt.candidate_capacity > 0) {
+        cap = 2;
+        while (cap < ix.opt.candidate_capacity) cap <<= 1;
+        while (cap < 2 * (int64_t)k) cap <<= 1;
+    }
+    return (int)cap;
+}
+
+static int make_workspace(Index &ix, int nq, int k, size_t out_rows, Workspace **out) {
+    Workspace *ws = nullptr;
+    {
+        std::lock_guard<std::mutex> g(ix.ws_mu);
+        if (!ix.ws_free.empty()) {
+            ws = ix.ws_free.back();
+            ix.ws_free.pop_back();
+        }
+    }
+    const int cap = candidate_capacity(ix, k);
+    int nq_cap = 16;
+    const int want = nq < SUB_BATCH ? nq : SUB_BATCH;
+    while (nq_cap < want) nq_cap <<= 1;
+    if (ws && (ws->nq_cap < nq_cap || ws->cap != cap || ws->dim_pad != ix.dim_pad || ws->out_cap < out_rows)) {
+        nq_cap = ws->nq_cap > nq_cap ? ws->nq_cap : nq_cap;
+        if (ws->out_cap > out_rows) out_rows = ws->out_cap;
+        delete ws;
+        ws = nullptr;
+    }
+    if (!ws) {
+        ws = new (std::nothrow) Workspace();
+        if (!ws) return fail(PKV_ERR_OOM, "out of host memory");
+        ws->device = ix.device;
+        ws->nq_cap = nq_cap;
+        ws->cap = cap;
+        ws->dim_pad = ix.dim_pad;
+        ws->out_cap = out_rows;
+        cudaError_t e = cudaSuccess;
+        auto A = [&](void **p, size_t bytes) {
+            if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 1);
+        };
+        if (cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) == cudaSuccess) ws->owns_stream = true;
+        ws->qraw_bytes = (size_t)nq_cap * ix.dim * 4;
+        A(&ws->d_qraw, ws->qraw_bytes);
+        A(&ws->d_q, (size_t)nq_cap * ix.dim_pad * 4);
+        A((void **)&ws->d_q_mag_f, sizeof(float) * nq_cap);
+        A((void **)&ws->d_q_mag_i, sizeof(int32_t) * nq_cap);
+        A((void **)&ws->d_cand, sizeof(uint64_t) * (size_t)nq_cap * cap);
+        A((void **)&ws->d_cnt, sizeof(uint32_t) * nq_cap);
+        A((void **)&ws->d_thr_key, sizeof(uint64_t) * nq_cap);
+        A((void **)&ws->d_thr_f, sizeof(float) * nq_cap);
+        A((void **)&ws->d_status, sizeof(SearchStatus));
+        A((void **)&ws->d_out_ids, sizeof(int64_t) * out_rows);
+        A((void **)&ws->d_out_dist, sizeof(float) * out_rows);
+        A((void **)&ws->d_out_counts, sizeof(int32_t) * (out_rows ? out_rows : 1));
+        if (e == cudaSuccess) e = cudaMallocHost((void **)&ws->h_status, sizeof(SearchStatus));
+        for (auto &ev : ws->ev)
+            if (e == cudaSuccess) e = cudaEventCreate(&ev);
+        if (e != cudaSuccess) {
+            delete ws;
+            cudaGetLastError();
+            return fail(e == cudaErrorMemoryAllocation ? PKV_ERR_OOM : PKV_ERR_CUDA, "workspace allocation failed: %s",
+                        cudaGetErrorString(e));
+        }
+    }
+    *out = ws;
+    return PKV_OK;
+}
+
+static void release_workspace(Index &ix, Workspace *ws) {
+    std::lock_guard<std::mutex> g(ix.ws_mu);
+    ix.ws_free.push_back(ws);
+}
+
+// ----------------------------------------------------------- search driver
+struct SearchRun {
+    Index &ix;
+    Workspace &ws;
+    cudaStream_t s;
+    ScanArgs args;
+    FilterSpec fs;
+    int nq, k;
+    int64_t safe_rows;
+    uint32_t min_filled = 0;
+    double scan_ms = 0;
+    int launches = 0, scan_launches = 0;
+    int depth_overflows = 0;
+};
+
+static int scan_range(SearchRun &r, int64_t b, int64_t e) {
+    r.args.row_begin = (uint32_t)b;
+    r.args.row_end = (uint32_t)e;
+    const bool timed = r.ix.opt.time_kernels != 0;
+    if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[0], r.s));
+    int n = 0;
+    PKV_TRY(launch_scan_simt(r.ix, r.args, r.s, &n));
+    r.launches += n;
+    r.scan_launches += n;
+    if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[1], r.s));
+    PKV_TRY(launch_select(r.ix, r.ws, r.nq, r.k, r.args.metric, r.fs, r.s));
+    r.launches += 2;
+    PKV_CUDA(cudaMemcpyAsync(r.ws.h_status, r.ws.d_status, sizeof(SearchStatus), cudaMemcpyDeviceToHost, r.s));
+    PKV_CUDA(cudaStreamSynchronize(r.s));
+    if (timed) {
+        float ms = 0.f;
+        PKV_CUDA(cudaEventElapsedTime(&ms, r.ws.ev[0], r.ws.ev[1]));
+        r.scan_ms += ms;
+    }
+    const SearchStatus st = *r.ws.h_status;
+    r.min_filled = st.min_filled;
+    if (st.any_overflow) {
+        // Some query pushed more candidates than its buffer holds.  The select kept the best k
+        // of what fitted (all real rows, so the thresholds only got tighter); re-scan the range
+        // in halves — duplicates are removed by the select — down to a size that cannot overflow.
+        if (e - b <= r.safe_rows)
+            return fail(PKV_ERR_CUDA, "internal: candidate overflow on a range of %lld rows (cap %d, k %d)",
+                        (long long)(e - b), r.ws.cap, r.k);
+        r.depth_overflows++;
+        int64_t mid = b + (e - b) / 2;
+        mid = (mid + 127) / 128 * 128;
+        if (mid <= b || mid >= e) mid = b + (e - b) / 2;
+        PKV_TRY(scan_range(r, b, mid));
+        PKV_TRY(scan_range(r, mid, e));
+    }
+    return PKV_OK;
+}
+
+// Queries already on the device in caller layout; outputs to device buffers.
+static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_qraw, int nq,
+                        const pkv_search_params &p, const uint64_t *d_bitmap, int64_t *d_ids, float *d_dist,
+                        int32_t *d_counts) {
+    const int64_t N = ix.sealed_rows;
+    const int k = p.k;
+    PKV_TRY(launch_prep_queries(ix, ws, d_qraw, nq, p.query_dtype, s));
+    PKV_TRY(launch_reset_state(ws, nq, s));
+    SearchRun r{ix, ws, s, ScanArgs{}, filter_spec_simt(ix.dtype, p.metric), nq, k, (int64_t)ws.cap - k};
+    r.launches = 2;
+    ScanArgs &a = r.args;
+    a.data = ix.d_data;
+    a.pitch_bytes = ix.pitch;
+    a.dim_pad = ix.dim_pad;
+    a.dim = ix.dim;
+    a.queries = ws.d_q;
+    a.q_mag_f = ws.d_q_mag_f;
+    a.q_mag_i = ws.d_q_mag_i;
+    a.row_mag_i = ix.d_mag_i;
+    a.row_mag_f = ix.d_mag_f;
+    a.nq = nq;
+    a.metric = p.metric;
+    a.topk.cand = ws.d_cand;
+    a.topk.cnt = ws.d_cnt;
+    a.topk.thr_key = ws.d_thr_key;
+    a.topk.thr_f = ws.d_thr_f;
+    a.topk.cap = (uint32_t)ws.cap;
+    a.topk.bitmap = d_bitmap;
+    a.topk.bitmap_stride = p.bitmap_stride_words;
+
+    // Chunk schedule: the first chunk (no threshold yet: every row is a candidate) is sized
+    // so it cannot overflow; afterwards a chunk of c rows behind `seen` scanned rows yields
+    // about k*c/seen candidates per query, so chunks grow geometrically.
+    double growth = (double)(ws.cap - k) / (3.0 * k);
+    if (ix.opt.chunk_growth_x100 > 0) growth = ix.opt.chunk_growth_x100 / 100.0;
+    if (growth < 0.25) growth = 0.25;
+    int64_t pos = 0;
+    r.min_filled = 0;
+    while (pos < N) {
+        int64_t chunk;
+        if (r.min_filled < (uint32_t)k) {
+            chunk = r.safe_rows;
+            if (pos == 0 && ix.opt.first_chunk_rows > 0 && ix.opt.first_chunk_rows < chunk)
+                chunk = ix.opt.first_chunk_rows;
+        } else {
+            chunk = (int64_t)((double)pos * growth);
+            if (chunk < r.safe_rows) chunk = r.safe_rows;
+        }
+        if (chunk >= 1024) chunk = chunk / 128 * 128;
+        if (chunk > N - pos) chunk = N - pos;
+        if (chunk < 1) chunk = 1;
+        PKV_TRY(scan_range(r, pos, pos + chunk));
+        pos += chunk;
+    }
+    PKV_TRY(launch_finalize(ix, ws, nq, k, d_ids, d_dist, d_counts, s));
+    r.launches += 1;
+    ix.n_launches += r.launches;
+    ix.n_scan_launches += r.scan_launches;
+    ix.n_fallback += r.depth_overflows;
+    ix.last_scan_ms += r.scan_ms;
+    ix.last_scan_kind = ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5);
+    return PKV_OK;
+}
+
+static int check_search_args(Index *ix, const void *queries, int nq, const pkv_search_params *p, const void *o_ids,
+                             const void *o_dist, const void *o_counts) {
+    if (!ix) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    if (!p) return fail(PKV_ERR_INVALID, "search params are NULL");
+    if (nq < 0) return fail(PKV_ERR_INVALID, "nq must be >= 0");
+    if (nq > 0 && (!queries || !o_ids || !o_dist || !o_counts))
+        return fail(PKV_ERR_INVALID, "queries/outputs must not be NULL");
+    if (p->k < 1) return fail(PKV_ERR_INVALID, "k must be a positive integer");
+    if (p->k > PKV_MAX_K) return fail(PKV_ERR_INVALID, "k %d exceeds PKV_MAX_K %d", p->k, PKV_MAX_K);
+    if (p->metric != PKV_L2 && p->metric != PKV_COSINE && p->metric != PKV_DOT)
+        return fail(PKV_ERR_INVALID, "unknown metric %d", p->metric);
+    const int qd = p->query_dtype;
+    const bool ok = (ix->dtype == PKV_F32 && qd == PKV_F32) || (ix->dtype == PKV_I8 && (qd == PKV_I8 || qd == PKV_F32)) ||
+                    (ix->dtype == PKV_F16 && (qd == PKV_F16 || qd == PKV_F32));
+    if (!ok) return fail(PKV_ERR_INVALID, "query dtype %d not accepted by an index of dtype %d", qd, ix->dtype);
+    if (ix->dtype == PKV_I8 && qd == PKV_F32 && !ix->has_scale)
+        return fail(PKV_ERR_NOT_READY, "int8 index has no scale artifact; cannot quantise f32 queries");
+    if (p->bitmap && p->bitmap_stride_words < 0) return fail(PKV_ERR_INVALID, "negative bitmap stride");
+    if (ix->sealed_rows != ix->rows)
+        return fail(PKV_ERR_NOT_READY, "index has %lld appended rows that are not sealed",
+                    (long long)(ix->rows - ix->sealed_rows));
+    return PKV_OK;
+}
+
+static int search_impl(Index &ix, const void *queries, bool host_io, int nq, const pkv_search_params &p,
+                       int64_t *out_ids, float *out_dist, int32_t *out_counts, cudaStream_t user_stream) {
+    PKV_TRY(use_device(ix.device));
+    std::shared_lock<std::shared_mutex> lock(ix.mu);
+    PKV_TRY(check_search_args(&ix, queries, nq, &p, out_ids, out_dist, out_counts));
+    if (nq == 0) return PKV_OK;
+    const int k = p.k;
+    const int qelem = elem_size(p.query_dtype);
+    Workspace *ws = nullptr;
+    const int sub = nq < SUB_BATCH ? nq : SUB_BATCH;
+    PKV_TRY(make_workspace(ix, nq, k, host_io ? (size_t)sub * k : 0, &ws));
+    cudaStream_t s = (!host_io && user_stream) ? user_stream : ws->stream;
+    struct Guard {
+        Index &ix;
+        Workspace *ws;
+        ~Guard() { release_workspace(ix, ws); }
+    } guard{ix, ws};
+    const int64_t words_per_bitmap = (ix.sealed_rows + 63) / 64;
+    ix.last_scan_ms = 0;
+    if (ix.opt.time_kernels) PKV_CUDA(cudaEventRecord(ws->ev[2], s));
+    for (int q0 = 0; q0 < nq; q0 += SUB_BATCH) {
+        const int n = nq - q0 < SUB_BATCH ? nq - q0 : SUB_BATCH;
+        const void *d_qraw;
+        const uint64_t *d_bitmap = nullptr;
+        int64_t *d_ids;
+        float *d_dist;
+        int32_t *d_counts;
+        pkv_search_params pp = p;
+        if (host_io) {
+            PKV_CUDA(cudaMemcpyAsync(ws->d_qraw, (const uint8_t *)queries + (size_t)q0 * ix.dim * qelem,
+                                     (size_t)n * ix.dim * qelem, cudaMemcpyHostToDevice, s));
+            d_qraw = ws->d_qraw;
+            if (p.bitmap) {
+                const size_t words = p.bitmap_stride_words ? (size_t)p.bitmap_stride_words * n : (size_t)words_per_bitmap;
+                if (p.bitmap_stride_words && p.bitmap_stride_words < words_per_bitmap)
+                    return fail(PKV_ERR_INVALID, "bitmap stride %lld words is shorter than the %lld words the rows need",
+                                (long long)p.bitmap_stride_words, (long long)words_per_bitmap);
+                if (ws->bitmap_bytes < words * 8) {
+                    cudaFree(ws->d_bitmap);
+                    ws->d_bitmap = nullptr;
+                    ws->bitmap_bytes = 0;
+                    PKV_CUDA(cudaMalloc((void **)&ws->d_bitmap, words * 8));
+                    ws->bitmap_bytes = words * 8;
+                }
+                PKV_CUDA(cudaMemcpyAsync(ws->d_bitmap, p.bitmap + (size_t)q0 * p.bitmap_stride_words, words * 8,
+                                         cudaMemcpyHostToDevice, s));
+                d_bitmap = ws->d_bitmap;
+            }
+            d_ids = ws->d_out_ids;
+            d_dist = ws->d_out_dist;
+            d_counts = ws->d_out_counts;
+        } else {
+            d_qraw = (const uint8_t *)queries + (size_t)q0 * ix.dim * qelem;
+            d_bitmap = p.bitmap ? p.bitmap + (size_t)q0 * p.bitmap_stride_words : nullptr;
+            d_ids = out_ids + (size_t)q0 * k;
+            d_dist = out_dist + (size_t)q0 * k;
+            d_counts = out_counts + q0;
+        }
+        PKV_TRY(search_batch(ix, *ws, s, d_qraw, n, pp, d_bitmap, d_ids, d_dist, d_counts));
+        if (host_io) {
+            PKV_CUDA(cudaMemcpyAsync(out_ids + (size_t)q0 * k, d_ids, sizeof(int64_t) * (size_t)n * k,
+                                     cudaMemcpyDeviceToHost, s));
+            PKV_CUDA(cudaMemcpyAsync(out_dist + (size_t)q0 * k, d_dist, sizeof(float) * (size_t)n * k,
+                                     cudaMemcpyDeviceToHost, s));
+            PKV_CUDA(cudaMemcpyAsync(out_counts + q0, d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (ix.opt.time_kernels) PKV_CUDA(cudaEventRecord(ws->ev[3], s));
+    PKV_CUDA(cudaStreamSynchronize(s));
+    if (ix.opt.time_kernels) {
+        float ms = 0.f;
+        PKV_CUDA(cudaEventElapsedTime(&ms, ws->ev[2], ws->ev[3]));
+        ix.last_total_ms = ms;
+    }
+    ix.n_searches += 1;
+    ix.n_queries += nq;
+    return PKV_OK;
+}
+
+// ------------------------------------------------------------ index storage
+static int grow(Index &ix, int64_t need_rows, bool exact = false) {
+    if (need_rows <= ix.cap_rows) return PKV_OK;
+    int64_t cap = ix.cap_rows > 0 ? ix.cap_rows + ix.cap_rows / 2 : 1024;
+    if (cap < need_rows || exact) cap = need_rows;
+    uint8_t *nd = nullptr;
+    int32_t *nmi = nullptr;
+    float *nmf = nullptr;
+    int64_t *nids = nullptr;
+    cudaError_t e = cudaMalloc((void **)&nd, (size_t)cap * ix.pitch);
+    if (e == cudaSuccess && ix.dtype == PKV_I8) e = cudaMalloc((void **)&nmi, sizeof(int32_t) * cap);
+    if (e == cudaSuccess && ix.dtype != PKV_I8) e = cudaMalloc((void **)&nmf, sizeof(float) * cap);
+    if (e == cudaSuccess && ix.d_ids) e = cudaMalloc((void **)&nids, sizeof(int64_t) * cap);
+    if (e != cudaSuccess) {
+        cudaFree(nd);
+        cudaFree(nmi);
+        cudaFree(nmf);
+        cudaFree(nids);
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? PKV_ERR_OOM : PKV_ERR_CUDA,
+                    "cannot reserve %lld rows (%lld bytes): %s", (long long)cap, (long long)(cap * ix.pitch),
+                    cudaGetErrorString(e));
+    }
+    if (ix.rows > 0) {
+        PKV_CUDA(cudaMemcpy(nd, ix.d_data, (size_t)ix.rows * ix.pitch, cudaMemcpyDeviceToDevice));
+        if (nmi) PKV_CUDA(cudaMemcpy(nmi, ix.d_mag_i, sizeof(int32_t) * ix.rows, cudaMemcpyDeviceToDevice));
+        if (nmf) PKV_CUDA(cudaMemcpy(nmf, ix.d_mag_f, sizeof(float) * ix.rows, cudaMemcpyDeviceToDevice));
+        if (nids) PKV_CUDA(cudaMemcpy(nids, ix.d_ids, sizeof(int64_t) * ix.rows, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(ix.d_data);
+    cudaFree(ix.d_mag_i);
+    cudaFree(ix.d_mag_f);
+    cudaFree(ix.d_ids);
+    ix.d_data = nd;
+    ix.d_mag_i = nmi;
+    ix.d_mag_f = nmf;
+    ix.d_ids = nids;
+    ix.cap_rows = cap;
+    return PKV_OK;
+}
+
+static int append_impl(Index &ix, const void *rows, const int64_t *row_ids, int64_t n, bool device_src) {
+    PKV_TRY(use_device(ix.device));
+    if (n < 0) return fail(PKV_ERR_INVALID, "n must be >= 0");
+    if (n == 0) return PKV_OK;
+    if (!rows) return fail(PKV_ERR_INVALID, "rows must not be NULL");
+    std::unique_lock<std::shared_mutex> lock(ix.mu);
+    if (ix.rows + n >= 0xFFFFFFF0ll) return fail(PKV_ERR_UNSUPPORTED, "an index shard holds at most 2^32-16 rows");
+    if (row_ids && !ix.d_ids) {
+        // first explicit ids: materialise the implicit ones of earlier rows
+        int64_t cap = ix.cap_rows > 0 ? ix.cap_rows : 1;
+        PKV_CUDA(cudaMalloc((void **)&ix.d_ids, sizeof(int64_t) * cap));
+        PKV_TRY(launch_fill_ids(ix.d_ids, 0, ix.rows, ix.row_base, nullptr));
+    }
+    PKV_TRY(grow(ix, ix.rows + n));
+    const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    uint8_t *dst = ix.d_data + (size_t)ix.rows * ix.pitch;
+    const size_t row_bytes = (size_t)ix.dim * ix.elem;
+    if ((int64_t)row_bytes == ix.pitch) {
+        PKV_CUDA(cudaMemcpy(dst, rows, (size_t)n * row_bytes, kind));
+    } else {
+        PKV_CUDA(cudaMemset(dst, 0, (size_t)n * ix.pitch));
+        PKV_CUDA(cudaMemcpy2D(dst, ix.pitch, rows, row_bytes, row_bytes, n, kind));
+    }
+    if (ix.d_ids) {
+        if (row_ids)
+            PKV_CUDA(cudaMemcpy(ix.d_ids + ix.rows, row_ids, sizeof(int64_t) * n, kind));
+        else
+            PKV_TRY(launch_fill_ids(ix.d_ids, ix.rows, ix.rows + n, ix.row_base, nullptr));
+    }
+    ix.rows += n;
+    PKV_CUDA(cudaDeviceSynchronize());
+    return PKV_OK;
+}
+
+}  // namespace pkv
+
+using namespace pkv;
+
+// =============================================================== C ABI
+extern "C" {
+
+int pkv_abi_version(void) { return PKV_ABI_VERSION; }
+
+const char *pkv_last_error(void) { return g_last_error.c_str(); }
+
+int pkv_device_count(int *count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (count) *count = 0;
+        return fail(PKV_ERR_CUDA, "no usable CUDA device: %s", cudaGetErrorString(e));
+    }
+    if (count) *count = c;
+    if (c == 0) return fail(PKV_ERR_CUDA, "no usable CUDA device: device count is 0");
+    return PKV_OK;
+}
+
+// ---- codec (host scalars are trivial pure functions; bulk work runs on the GPU)
+float pkv_scale_from_absmax(float absmax) {
+    if (absmax > 0.0f && absmax <= 3.402823466e+38f) return absmax / 127.0f;
+    return 1.0f;
+}
+void pkv_scale_artifact(float scale, uint8_t out[4]) {
+    uint32_t bits;
+    memcpy(&bits, &scale, 4);
+    for (int i = 0; i < 4; ++i) out[i] = (uint8_t)(bits >> (8 * i));
+}
+int pkv_artifact_scale(const uint8_t *artifact, size_t len, float *scale) {
+    if (!artifact || len != 4) return fail(PKV_ERR_INVALID, "scale artifact must be exactly 4 bytes (got %zu)", len);
+    uint32_t bits = (uint32_t)artifact[0] | ((uint32_t)artifact[1] << 8) | ((uint32_t)artifact[2] << 16) |
+                    ((uint32_t)artifact[3] << 24);
+    float s;
+    memcpy(&s, &bits, 4);
+    if (!(s > 0.0f) || !(s <= 3.402823466e+38f))
+        return fail(PKV_ERR_INVALID, "scale artifact is not a positive finite f32");
+    if (scale) *scale = s;
+    return PKV_OK;
+}
+
+int pkv_blob_absmax_device(int device, const float *d_values, int64_t n, float *absmax, void *stream) {
+    PKV_TRY(use_device(device));
+    if (n < 0 || (n > 0 && !d_values) || !absmax) return fail(PKV_ERR_INVALID, "bad arguments");
+    float *d_out = nullptr;
+    PKV_CUDA(cudaMalloc((void **)&d_out, sizeof(float)));
+    int st = launch_absmax(d_values, n, d_out, (cudaStream_t)stream);
+    if (st == PKV_OK) {
+        cudaError_t e = cudaMemcpyAsync(absmax, d_out, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) st = fail(PKV_ERR_CUDA, "absmax readback failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_out);
+    return st;
+}
+
+int pkv_blob_absmax(int device, const float *values, int64_t n, float *absmax) {
+    PKV_TRY(use_device(device));
+    if (n < 0 || (n > 0 && !values) || !absmax) return fail(PKV_ERR_INVALID, "bad arguments");
+    float *d = nullptr;
+    PKV_CUDA(cudaMalloc((void **)&d, sizeof(float) * (n > 0 ? n : 1)));
+    cudaError_t e = cudaMemcpy(d, values, sizeof(float) * n, cudaMemcpyHostToDevice);
+    int st = e == cudaSuccess ? pkv_blob_absmax_device(device, d, n, absmax, nullptr)
+                              : fail(PKV_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    cudaFree(d);
+    return st;
+}
+
+int pkv_quantize_int8_device(int device, const float *d_values, int64_t n, float scale, int8_t *d_codes,
+                             void *stream) {
+    PKV_TRY(use_device(device));
+    if (n < 0 || (n > 0 && (!d_values || !d_codes))) return fail(PKV_ERR_INVALID, "bad arguments");
+    if (!(scale > 0.0f) || !(scale <= 3.402823466e+38f))
+        return fail(PKV_ERR_INVALID, "scale must be a positive finite f32");
+    PKV_TRY(launch_quantize(d_values, n, scale, d_codes, (cudaStream_t)stream));
+    PKV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return PKV_OK;
+}
+
+int pkv_quantize_int8(int device, const float *values, int64_t n, float scale, int8_t *codes) {
+    PKV_TRY(use_device(device));
+    if (n < 0 || (n > 0 && (!values || !codes))) return fail(PKV_ERR_INVALID, "bad arguments");
+    if (n == 0) return PKV_OK;
+    float *d = nullptr;
+    int8_t *c = nullptr;
+    PKV_CUDA(cudaMalloc((void **)&d, sizeof(float) * n));
+    cudaError_t e = cudaMalloc((void **)&c, n);
+    if (e == cudaSuccess) e = cudaMemcpy(d, values, sizeof(float) * n, cudaMemcpyHostToDevice);
+    int st = e == cudaSuccess ? pkv_quantize_int8_device(device, d, n, scale, c, nullptr)
+                              : fail(PKV_ERR_CUDA, "quantize staging failed: %s", cudaGetErrorString(e));
+    if (st == PKV_OK) {
+        e = cudaMemcpy(codes, c, n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) st = fail(PKV_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    cudaFree(c);
+    return st;
+}
+
+// ---- index lifecycle
+int pkv_index_create(int device, int dim, int dtype, pkv_index **out) {
+    if (!out) return fail(PKV_ERR_INVALID, "out must not be NULL");
+    *out = nullptr;
+    if (dim < 1 || dim > 4096) return fail(PKV_ERR_INVALID, "dim %d out of range (1..4096)", dim);
+    if (dtype != PKV_F32 && dtype != PKV_I8 && dtype != PKV_F16) return fail(PKV_ERR_INVALID, "unknown dtype %d", dtype);
+    PKV_TRY(use_device(device));
+    cudaDeviceProp prop;
+    PKV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PKV_ERR_UNSUPPORTED, "device %d is sm_%d%d; libpkv is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    Index *ix = new (std::nothrow) Index();
+    if (!ix) return fail(PKV_ERR_OOM, "out of host memory");
+    ix->device = device;
+    ix->dim = dim;
+    ix->dtype = dtype;
+    ix->elem = elem_size(dtype);
+    ix->dim_pad = pad_dim(dim, dtype);
+    ix->pitch = (int64_t)ix->dim_pad * ix->elem;
+    ix->sm_count = prop.multiProcessorCount;
+    *out = reinterpret_cast<pkv_index *>(ix);
+    return PKV_OK;
+}
+
+int pkv_index_destroy(pkv_index *h) {
+    if (!h) return PKV_OK;
+    Index *ix = reinterpret_cast<Index *>(h);
+    cudaSetDevice(ix->device);
+    for (Workspace *ws : ix->ws_free) delete ws;
+    cudaFree(ix->d_data);
+    cudaFree(ix->d_ids);
+    cudaFree(ix->d_mag_i);
+    cudaFree(ix->d_mag_f);
+    delete ix;
+    return PKV_OK;
+}
+
+int pkv_index_reserve(pkv_index *h, int64_t rows) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    PKV_TRY(use_device(ix.device));
+    if (rows < 0) return fail(PKV_ERR_INVALID, "rows must be >= 0");
+    std::unique_lock<std::shared_mutex> lock(ix.mu);
+    if (rows <= ix.cap_rows) return PKV_OK;
+    return grow(ix, rows, /*exact=*/true);  // no 1.5x headroom when the caller states the size
+}
+
+int pkv_index_append(pkv_index *h, const void *rows, const int64_t *row_ids, int64_t n) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    return append_impl(*reinterpret_cast<Index *>(h), rows, row_ids, n, false);
+}
+int pkv_index_append_device(pkv_index *h, const void *d_rows, const int64_t *d_row_ids, int64_t n) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    return append_impl(*reinterpret_cast<Index *>(h), d_rows, d_row_ids, n, true);
+}
+
+int pkv_index_set_scale(pkv_index *h, const uint8_t *artifact, size_t len) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    if (ix.dtype != PKV_I8) return fail(PKV_ERR_INVALID, "only int8 indexes carry a scale artifact");
+    float s = 0.f;
+    PKV_TRY(pkv_artifact_scale(artifact, len, &s));
+    std::unique_lock<std::shared_mutex> lock(ix.mu);
+    ix.scale = s;
+    ix.has_scale = true;
+    return PKV_OK;
+}
+
+int pkv_index_set_row_base(pkv_index *h, int64_t row_base) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    std::unique_lock<std::shared_mutex> lock(ix.mu);
+    if (ix.d_ids && ix.rows > 0)
+        return fail(PKV_ERR_INVALID, "row_base must be set before rows with explicit ids are appended");
+    ix.row_base = row_base;
+    return PKV_OK;
+}
+
+int pkv_index_seal(pkv_index *h) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    PKV_TRY(use_device(ix.device));
+    std::unique_lock<std::shared_mutex> lock(ix.mu);
+    if (ix.sealed_rows < ix.rows) {
+        PKV_TRY(launch_row_mags(ix, ix.sealed_rows, ix.rows, nullptr));
+        PKV_CUDA(cudaDeviceSynchronize());
+        ix.sealed_rows = ix.rows;
+    }
+    return PKV_OK;
+}
+
+int pkv_index_get_info(const pkv_index *h, pkv_index_info *info) {
+    if (!h || !info) return fail(PKV_ERR_INVALID, "NULL argument");
+    const Index &ix = *reinterpret_cast<const Index *>(h);
+    memset(info, 0, sizeof(*info));
+    info->abi_version = PKV_ABI_VERSION;
+    info->device = ix.device;
+    info->dim = ix.dim;
+    info->dtype = ix.dtype;
+    info->sealed = ix.sealed_rows == ix.rows ? 1 : 0;
+    info->has_scale = ix.has_scale ? 1 : 0;
+    info->scale = ix.scale;
+    info->rows = ix.rows;
+    info->capacity_rows = ix.cap_rows;
+    info->device_bytes = ix.cap_rows * (ix.pitch + 4 + (ix.d_ids ? 8 : 0));
+    info->row_base = ix.row_base;
+    return PKV_OK;
+}
+
+int pkv_search(pkv_index *h, const void *queries, int nq, const pkv_search_params *params, int64_t *out_ids,
+               float *out_dist, int32_t *out_counts) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    if (!params) return fail(PKV_ERR_INVALID, "search params are NULL");
+    return search_impl(*reinterpret_cast<Index *>(h), queries, true, nq, *params, out_ids, out_dist, out_counts,
+                       nullptr);
+}
+
+int pkv_search_device(pkv_index *h, const void *d_queries, int nq, const pkv_search_params *params, int64_t *d_out_ids,
+                      float *d_out_dist, int32_t *d_out_counts, void *stream) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    if (!params) return fail(PKV_ERR_INVALID, "search params are NULL");
+    return search_impl(*reinterpret_cast<Index *>(h), d_queries, false, nq, *params, d_out_ids, d_out_dist,
+                       d_out_counts, (cudaStream_t)stream);
+}
+
+int pkv_merge_topk_device(int device, const int64_t *d_ids, const float *d_dist, int parts, int nq, int k,
+                          int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts, void *stream) {
+    PKV_TRY(use_device(device));
+    if (parts < 1 || parts > 256 || nq < 0 || k < 1) return fail(PKV_ERR_INVALID, "bad merge shape");
+    if (nq > 0 && (!d_ids || !d_dist || !d_out_ids || !d_out_dist || !d_out_counts))
+        return fail(PKV_ERR_INVALID, "NULL buffer");
+    PKV_TRY(launch_merge(d_ids, d_dist, parts, nq, k, d_out_ids, d_out_dist, d_out_counts, (cudaStream_t)stream));
+    PKV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return PKV_OK;
+}
+
+int pkv_aggregate_device(int device, const float *d_dist, const int64_t *d_item_of_row, const float *d_weights,
+                         int64_t n, int64_t n_items, int agg, double *d_out, void *stream) {
+    PKV_TRY(use_device(device));
+    if (n < 0 || n_items < 0 || agg < 0 || agg > 2) return fail(PKV_ERR_INVALID, "bad aggregate arguments");
+    if ((n > 0 && (!d_dist || !d_item_of_row)) || (n_items > 0 && !d_out)) return fail(PKV_ERR_INVALID, "NULL buffer");
+    PKV_TRY(launch_aggregate(d_dist, d_item_of_row, d_weights, n, n_items, agg, d_out, (cudaStream_t)stream));
+    PKV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return PKV_OK;
+}
+
+int pkv_index_counters(pkv_index *h, pkv_counters *out) {
+    if (!h || !out) return fail(PKV_ERR_INVALID, "NULL argument");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    memset(out, 0, sizeof(*out));
+    out->searches = ix.n_searches;
+    out->queries = ix.n_queries;
+    out->kernel_launches = ix.n_launches;
+    out->scan_launches = ix.n_scan_launches;
+    out->fallback_queries = ix.n_fallback;
+    out->last_scan_ms = ix.last_scan_ms;
+    out->last_total_ms = ix.last_total_ms;
+    out->last_scan_kind = ix.last_scan_kind;
+    return PKV_OK;
+}
+
+int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
+    if (!h || !name) return fail(PKV_ERR_INVALID, "NULL argument");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    std::unique_lock<std::shared_mutex> lock(ix.mu);
+    if (!strcmp(name, "force_simt")) ix.opt.force_simt = (int)value;
+    else if (!strcmp(name, "candidate_capacity")) ix.opt.candidate_capacity = value;
+    else if (!strcmp(name, "first_chunk_rows")) ix.opt.first_chunk_rows = value;
+    else if (!strcmp(name, "chunk_growth_x100")) ix.opt.chunk_growth_x100 = value;
+    else if (!strcmp(name, "time_kernels")) ix.opt.time_kernels = (int)value;
+    else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
+    return PKV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+// pkv_internal.cuh — shared declarations of the libpkv translation units.
+//
+// Data layout in HBM:
+//   corpus    : row-major, one row per stored vector, row pitch = dim padded with zeros to a
+//               multiple of 128 bytes (f32: 32 comps, f16: 64, i8: 128) so every row starts on
+//               a 128-byte line and a K-chunk is one TMA/UMMA swizzle atom.  Zero padding
+//               changes neither dot products nor norms nor L2.
+//   row_ids   : optional int64 per row (item_data.id); absent => row_base + position.
+//   row_norm  : int32 sum of squares per row for int8 (exact), f32 for the tensor-core f32 path.
+//   candidates: per query a buffer of `cap` packed 64-bit keys
+//               (ordered f32 distance << 32 | local row); see pack_key().
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pkv.h"
+
+namespace pkv {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+
+#define PKV_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            return ::pkv::fail(_e == cudaErrorMemoryAllocation ? PKV_ERR_OOM : PKV_ERR_CUDA,        \
+                               "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                               __LINE__);                                                           \
+        }                                                                                           \
+    } while (0)
+
+#define PKV_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != PKV_OK) return _s;  \
+    } while (0)
+
+// ------------------------------------------------------------- key packing
+// Total order of the contract: ascending f32 distance, NaN last, ties by ascending row.
+// -0.0 is canonicalised to +0.0 so that equal distances really tie.
+__host__ __device__ inline uint32_t ordered_bits(float d) {
+    if (d != d) return 0xFFFFFFFFu;
+    d += 0.0f;
+    uint32_t b;
+#ifdef __CUDA_ARCH__
+    b = __float_as_uint(d);
+#else
+    memcpy(&b, &d, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float unordered_bits(uint32_t o) {
+    if (o == 0xFFFFFFFFu) {
+#ifdef __CUDA_ARCH__
+        return __uint_as_float(0x7FC00000u);
+#else
+        uint32_t n = 0x7FC00000u;
+        float f;
+        memcpy(&f, &n, 4);
+        return f;
+#endif
+    }
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+__host__ __device__ inline uint64_t pack_key(float d, uint32_t row) {
+    return ((uint64_t)ordered_bits(d) << 32) | row;
+}
+static constexpr uint64_t KEY_MAX = 0xFFFFFFFFFFFFFFFFull;
+
+// --------------------------------------------------------- filter kinds
+// How a scan kernel turns the exact k-th best distance d_k into the cheap
+// threshold `thr_f` it compares its own (approximate) per-pair figure against.
+// The kernel passes a pair on to the exact key computation iff !(f > thr_f).
+enum FilterKind : int {
+    FK_EXACT_DIST = 0,  // f is the final distance itself (f32 DOT, int8 DOT): thr_f = d_k
+    FK_COS_RATIO = 1,   // f = -dot / sqrt(aMag); thr_f = -(1 - d_k - 2.4e-7) * sqrt(bMag) + slack
+    FK_L2_SQUARED = 2,  // f = squared L2; thr_f = d_k^2 * (1 + rel) + abs
+};
+
+struct FilterSpec {
+    int kind;
+    float rel;  // relative slack on the threshold
+    float abs;  // absolute slack, in units of the filter figure (scaled by sqrt(bMag) for FK_COS_RATIO)
+};
+
+// ------------------------------------------------------------ device state
+struct TopkDev {
+    uint64_t *cand;          // [nq][cap]
+    uint32_t *cnt;           // [nq] raw number of pushes (may exceed cap: overflow)
+    const uint64_t *thr_key; // [nq] exact key of the current k-th best (KEY_MAX while < k found)
+    const float *thr_f;      // [nq] filter-domain threshold
+    uint32_t cap;
+    const uint64_t *bitmap;  // optional membership bits over local rows
+    int64_t bitmap_stride;   // words per query, 0 = shared
+};
+
+struct ScanArgs {
+    const void *data;       // corpus base
+    int64_t pitch_bytes;    // row pitch in bytes
+    uint32_t row_begin, row_end;
+    int dim_pad;            // padded components per row
+    int dim;                // true components per row
+    const void *queries;    // [nq][dim_pad], index dtype (f16 index: f32 queries)
+    const float *q_mag_f;   // [nq] f32 path: sum q^2 (sequential f32, as the reference accumulates bMag)
+    const int32_t *q_mag_i; // [nq] int8 path: exact integer sum q^2
+    const int32_t *row_mag_i; // [rows] int8 path: exact integer sum a^2
+    const float *row_mag_f;   // [rows] tensor-core f32 path
+    int nq;
+    int metric;
+    TopkDev topk;
+};
+
+struct SearchStatus {  // device -> pinned host after every chunk
+    uint32_t max_raw_cnt;
+    uint32_t any_overflow;
+    uint32_t min_filled;
+    uint32_t pad;
+};
+
+// --------------------------------------------------------------- host side
+struct Workspace {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int nq_cap = 0, dim_pad = 0, cap = 0;
+    void *d_qraw = nullptr;       // raw queries as the caller laid them out
+    size_t qraw_bytes = 0;
+    void *d_q = nullptr;          // padded queries in scan dtype
+    float *d_q_mag_f = nullptr;
+    int32_t *d_q_mag_i = nullptr;
+    uint64_t *d_cand = nullptr;
+    uint32_t *d_cnt = nullptr;
+    uint64_t *d_thr_key = nullptr;
+    float *d_thr_f = nullptr;
+    SearchStatus *d_status = nullptr;
+    SearchStatus *h_status = nullptr;  // pinned
+    int64_t *d_out_ids = nullptr;
+    float *d_out_dist = nullptr;
+    int32_t *d_out_counts = nullptr;
+    uint64_t *d_bitmap = nullptr;
+    size_t bitmap_bytes = 0;
+    size_t out_cap = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Workspace();
+};
+
+struct Options {
+    int force_simt = 0;
+    int64_t candidate_capacity = 0;  // 0 = auto
+    int64_t first_chunk_rows = 0;    // 0 = auto
+    int64_t chunk_growth_x100 = 0;   // 0 = auto
+    int time_kernels = 1;
+};
+
+struct Index {
+    int device = 0;
+    int dim = 0, dim_pad = 0;
+    int dtype = PKV_F32;
+    int elem = 4;
+    int64_t pitch = 0;  // bytes
+    int64_t rows = 0, cap_rows = 0, sealed_rows = 0;
+    int64_t row_base = 0;
+    uint8_t *d_data = nullptr;
+    int64_t *d_ids = nullptr;   // null until some append carries ids
+    int64_t ids_rows = 0;       // rows of d_ids that are initialised
+    int32_t *d_mag_i = nullptr; // int8 row sums of squares
+    float *d_mag_f = nullptr;   // f32/f16 row sums of squares (tensor-core paths)
+    bool has_scale = false;
+    float scale = 1.0f;
+    int sm_count = 148;
+    Options opt;
+    std::shared_mutex mu;       // searches shared, append/seal exclusive
+    std::mutex ws_mu;
+    std::vector<Workspace *> ws_free;
+    // counters
+    std::atomic<int64_t> n_searches{0}, n_queries{0}, n_launches{0}, n_scan_launches{0}, n_fallback{0};
+    double last_scan_ms = 0, last_total_ms = 0;
+    int last_scan_kind = 0;
+};
+
+// ---- kernels / launchers (each returns a pkv_status) ----
+// pkv_scan_simt.cu
+int launch_scan_simt(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches);
+// pkv_topk.cu
+int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);
+int launch_reset_state(Workspace &ws, int nq, cudaStream_t s);
+int launch_select(const Index &ix, Workspace &ws, int nq, int k, int metric, FilterSpec fs, cudaStream_t s);
+int launch_finalize(const Index &ix, Workspace &ws, int nq, int k, int64_t *d_ids, float *d_dist, int32_t *d_counts,
+                    cudaStream_t s);
+int launch_row_mags(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);
+int launch_merge(const int64_t *d_ids, const float *d_dist, int parts, int nq, int k, int64_t *o_ids, float *o_dist,
+                 int32_t *o_counts, cudaStream_t s);
+int launch_aggregate(const float *d_dist, const int64_t *d_item, const float *d_w, int64_t n, int64_t n_items, int agg,
+                     double *d_out, cudaStream_t s);
+int launch_absmax(const float *d_values, int64_t n, float *d_out, cudaStream_t s);
+int launch_quantize(const float *d_values, int64_t n, float scale, int8_t *d_codes, cudaStream_t s);
+int launch_fill_ids(int64_t *d_ids, int64_t begin, int64_t end, int64_t base, cudaStream_t s);
+
+FilterSpec filter_spec_simt(int dtype, int metric);
+
+}  // namespace pkv

@@ -1,0 +1,231 @@
+// pkv_policy.cpp — host-side mirror of the PQL vector-filter policy, in C++ because the
+// reference's host side is compiled Rust and no Rust toolchain exists in this image.
+// Same names, argument meaning and error text as:
+//   pql/builder/filters/embedding_types.rs  (IndexMode, DistanceFunction, DistanceAggregation, default_k)
+//   pql/preprocess.rs:314-465               (resolve_vector_quant, quant_requested, normalize_variant,
+//                                            validate_quant_args)
+//   db/vector_quants.rs:1784-1869           (ReadyPair / resolve_ready_pair)
+// (paths relative to /root/reference/panoptikon/src)
+#include <cctype>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pkv.h"
+
+namespace pkv {
+int fail(int code, const char *fmt, ...);
+}
+using pkv::fail;
+
+namespace {
+
+// normalize_variant (preprocess.rs:425-431): blank / whitespace-only names mean "unset".
+bool normalize_variant(const char *variant, std::string *out) {
+    if (!variant) return false;
+    const char *b = variant;
+    const char *e = variant + strlen(variant);
+    while (b < e && isspace((unsigned char)*b)) ++b;
+    while (e > b && isspace((unsigned char)e[-1])) --e;
+    if (b == e) return false;
+    if (out) out->assign(b, e);
+    return true;
+}
+
+std::string lower(const char *s) {
+    std::string r(s);
+    for (auto &c : r) c = (char)tolower((unsigned char)c);
+    return r;
+}
+
+struct QuantEntry {
+    pkv_ready_pair pair;
+    pkv_index *index;
+};
+
+}  // namespace
+
+struct pkv_space {
+    std::string model;
+    pkv_index *exact = nullptr;
+    std::map<std::string, QuantEntry> profiles;  // name -> ready pair (absent = not ready)
+    std::string default_profile;                 // "" = no default configured
+    std::mutex mu;
+};
+
+extern "C" {
+
+int pkv_parse_index_mode(const char *name, int *mode) {
+    if (!name || !mode) return fail(PKV_ERR_INVALID, "NULL argument");
+    // serde rename_all = "lowercase" (embedding_types.rs:50-58)
+    if (!strcmp(name, "auto")) *mode = PKV_INDEX_AUTO;
+    else if (!strcmp(name, "exact")) *mode = PKV_INDEX_EXACT;
+    else if (!strcmp(name, "quant")) *mode = PKV_INDEX_QUANT;
+    else if (!strcmp(name, "ann")) *mode = PKV_INDEX_ANN;
+    else return fail(PKV_ERR_INVALID, "unknown variant `%s`, expected one of `auto`, `exact`, `quant`, `ann`", name);
+    return PKV_OK;
+}
+
+int pkv_parse_distance_function(const char *name, int case_insensitive, int *metric) {
+    if (!name || !metric) return fail(PKV_ERR_INVALID, "NULL argument");
+    // serde names "L2"/"COSINE" (embedding_types.rs:20-26); from_override lowercases (:28-36)
+    std::string n = case_insensitive ? lower(name) : std::string(name);
+    if (n == (case_insensitive ? "l2" : "L2")) *metric = PKV_L2;
+    else if (n == (case_insensitive ? "cosine" : "COSINE")) *metric = PKV_COSINE;
+    else return fail(PKV_ERR_INVALID, "unknown variant `%s`, expected `L2` or `COSINE`", name);
+    return PKV_OK;
+}
+
+int pkv_parse_distance_aggregation(const char *name, int *agg) {
+    if (!name || !agg) return fail(PKV_ERR_INVALID, "NULL argument");
+    if (!strcmp(name, "MIN")) *agg = PKV_AGG_MIN;
+    else if (!strcmp(name, "MAX")) *agg = PKV_AGG_MAX;
+    else if (!strcmp(name, "AVG")) *agg = PKV_AGG_AVG;
+    else return fail(PKV_ERR_INVALID, "unknown variant `%s`, expected one of `MIN`, `MAX`, `AVG`", name);
+    return PKV_OK;
+}
+
+// preprocess.rs:436-446
+int pkv_validate_quant_args(int index_mode, int64_t k) {
+    if (index_mode < PKV_INDEX_AUTO || index_mode > PKV_INDEX_ANN) return fail(PKV_ERR_INVALID, "unknown index mode");
+    if (index_mode == PKV_INDEX_ANN) return fail(PKV_ERR_INVALID, "index \"ann\" is reserved and not yet available");
+    if (k < 1) return fail(PKV_ERR_INVALID, "k must be a positive integer");
+    return PKV_OK;
+}
+
+// preprocess.rs:413-421
+int pkv_quant_requested(int index_mode, const char *variant_or_null) {
+    (void)variant_or_null;
+    switch (index_mode) {
+        case PKV_INDEX_EXACT: return 0;
+        case PKV_INDEX_ANN: return 0;
+        case PKV_INDEX_AUTO:
+        case PKV_INDEX_QUANT: return 1;
+        default: return 0;
+    }
+}
+
+// preprocess.rs:331-332
+int pkv_quant_strict(int index_mode, const char *variant_or_null) {
+    return (index_mode == PKV_INDEX_QUANT || normalize_variant(variant_or_null, nullptr)) ? 1 : 0;
+}
+
+int pkv_space_create(const char *model, pkv_index *exact_f32, pkv_space **out) {
+    if (!model || !out) return fail(PKV_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (exact_f32) {
+        pkv_index_info info;
+        int st = pkv_index_get_info(exact_f32, &info);
+        if (st != PKV_OK) return st;
+        if (info.dtype != PKV_F32) return fail(PKV_ERR_INVALID, "the exact index of a space must be PKV_F32");
+    }
+    pkv_space *s = new (std::nothrow) pkv_space();
+    if (!s) return fail(PKV_ERR_OOM, "out of host memory");
+    s->model = model;
+    s->exact = exact_f32;
+    *out = s;
+    return PKV_OK;
+}
+
+int pkv_space_destroy(pkv_space *s) {
+    delete s;
+    return PKV_OK;
+}
+
+int pkv_space_set_quant(pkv_space *s, const char *profile_name, int is_default, const pkv_ready_pair *pair,
+                        pkv_index *quant_i8) {
+    if (!s || !profile_name) return fail(PKV_ERR_INVALID, "NULL argument");
+    std::string name;
+    if (!normalize_variant(profile_name, &name)) return fail(PKV_ERR_INVALID, "profile names are never empty");
+    std::lock_guard<std::mutex> g(s->mu);
+    if (is_default) s->default_profile = name;
+    if (!pair || !quant_i8) {  // withdraw: the pair is no longer ready
+        s->profiles.erase(name);
+        return PKV_OK;
+    }
+    pkv_index_info info;
+    int st = pkv_index_get_info(quant_i8, &info);
+    if (st != PKV_OK) return st;
+    if (info.dtype != PKV_I8) return fail(PKV_ERR_INVALID, "a quant profile index must be PKV_I8");
+    // a pair is only usable with a positive finite scale and a dimension (vector_quants.rs:1846-1850)
+    if (!(pair->scale > 0.0f) || !(pair->scale <= 3.402823466e+38f) || pair->dim < 1)
+        return fail(PKV_ERR_INVALID, "ready pair needs a positive finite scale and a dimension");
+    if (info.dim != pair->dim)
+        return fail(PKV_ERR_DIM_MISMATCH, "quant index dimension %d does not match the pair's %lld", info.dim,
+                    (long long)pair->dim);
+    s->profiles[name] = QuantEntry{*pair, quant_i8};
+    return PKV_OK;
+}
+
+// resolve_vector_quant (preprocess.rs:314-393) followed by the scan the compiled SQL would run.
+int pkv_space_search(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
+                     const char *variant_or_null, int64_t k_arg, int depth, int64_t *out_ids, float *out_dist,
+                     int32_t *out_counts, int64_t *used_profile_id) {
+    if (!s) return fail(PKV_ERR_INVALID, "space handle is NULL");
+    if (used_profile_id) *used_profile_id = -1;
+    int st = pkv_validate_quant_args(index_mode, k_arg);
+    if (st != PKV_OK) return st;
+    if (metric != PKV_L2 && metric != PKV_COSINE)
+        return fail(PKV_ERR_INVALID, "distance function must be L2 or COSINE");
+    if (depth < 1) return fail(PKV_ERR_INVALID, "k must be a positive integer");
+
+    QuantEntry chosen{};
+    bool use_quant = false;
+    if (pkv_quant_requested(index_mode, variant_or_null)) {
+        std::string variant;
+        const bool named = normalize_variant(variant_or_null, &variant);
+        const bool strict = index_mode == PKV_INDEX_QUANT || named;
+        std::lock_guard<std::mutex> g(s->mu);
+        std::string profile_name = named ? variant : s->default_profile;
+        if (profile_name.empty()) {
+            if (strict) return fail(PKV_ERR_INVALID, "no default vector quant profile is configured");
+        } else {
+            auto it = s->profiles.find(profile_name);
+            if (it == s->profiles.end()) {
+                if (strict)
+                    return fail(PKV_ERR_NOT_READY,
+                                "vector quant profile '%s' does not exist or is not ready for model '%s'",
+                                profile_name.c_str(), s->model.c_str());
+            } else if ((int64_t)query_dim != it->second.pair.dim) {
+                if (strict)
+                    return fail(PKV_ERR_DIM_MISMATCH,
+                                "query embedding dimension mismatch for model '%s' (expected %lld, got %d)",
+                                s->model.c_str(), (long long)it->second.pair.dim, query_dim);
+            } else {
+                chosen = it->second;
+                use_quant = true;
+            }
+        }
+    }
+
+    pkv_search_params p;
+    memset(&p, 0, sizeof(p));
+    p.metric = metric;
+    p.k = depth > PKV_MAX_K ? PKV_MAX_K : depth;
+    p.query_dtype = PKV_F32;
+    if (use_quant) {
+        // compute_query_quant with the pair's frozen scale happens on the GPU inside pkv_search
+        // (f32 queries against an int8 index); the index must carry that same scale.
+        pkv_index_info info;
+        st = pkv_index_get_info(chosen.index, &info);
+        if (st != PKV_OK) return st;
+        if (!info.has_scale || info.scale != chosen.pair.scale)
+            return fail(PKV_ERR_NOT_READY, "quant index scale does not match the ready pair's frozen scale");
+        st = pkv_search(chosen.index, queries, nq, &p, out_ids, out_dist, out_counts);
+        if (st == PKV_OK && used_profile_id) *used_profile_id = chosen.pair.profile_id;
+        return st;
+    }
+    if (!s->exact) return fail(PKV_ERR_NOT_READY, "space '%s' has no exact index", s->model.c_str());
+    pkv_index_info info;
+    st = pkv_index_get_info(s->exact, &info);
+    if (st != PKV_OK) return st;
+    if (info.dim != query_dim)
+        return fail(PKV_ERR_DIM_MISMATCH, "query embedding dimension mismatch for model '%s' (expected %d, got %d)",
+                    s->model.c_str(), info.dim, query_dim);
+    return pkv_search(s->exact, queries, nq, &p, out_ids, out_dist, out_counts);
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+"""VectorIndex: the corpus of one embedding setter resident in one B200's HBM, searched by
+libpkv's sm_100a kernels.  Thin wrapper over the C ABI (include/pkv.h); accepts NumPy arrays
+(host path: H2D/D2H inside the call) or torch CUDA tensors (device path)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+
+_NP = {N.F32: np.float32, N.I8: np.int8, N.F16: np.float16}
+_CODE = {np.dtype(np.float32): N.F32, np.dtype(np.int8): N.I8, np.dtype(np.float16): N.F16}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _torch_code(t) -> int:
+    import torch
+
+    return {torch.float32: N.F32, torch.int8: N.I8, torch.float16: N.F16}[t.dtype]
+
+
+class VectorIndex:
+    def __init__(self, dim: int, dtype: int = N.F32, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().pkv_index_create(device, dim, dtype, C.byref(self._h)))
+        self.dim, self.dtype, self.device = dim, dtype, device
+
+    # -- lifecycle -----------------------------------------------------------
+    def close(self) -> None:
+        if self._h:
+            N.lib().pkv_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reserve(self, rows: int) -> None:
+        N.check(N.lib().pkv_index_reserve(self._h, rows))
+
+    def append(self, rows, row_ids=None) -> None:
+        """rows: [n, dim] array of the index dtype — NumPy (host) or torch CUDA tensor."""
+        if _is_torch(rows):
+            assert rows.is_cuda and rows.is_contiguous() and rows.dim() == 2 and rows.shape[1] == self.dim
+            assert _torch_code(rows) == self.dtype
+            ids_ptr = None
+            if row_ids is not None:
+                import torch
+
+                assert row_ids.is_cuda and row_ids.dtype == torch.int64 and row_ids.is_contiguous()
+                ids_ptr = C.c_void_p(row_ids.data_ptr())
+            N.check(N.lib().pkv_index_append_device(self._h, C.c_void_p(rows.data_ptr()), ids_ptr, rows.shape[0]))
+            return
+        rows = np.ascontiguousarray(rows, dtype=_NP[self.dtype])
+        assert rows.ndim == 2 and rows.shape[1] == self.dim
+        ids = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.int64)
+        assert ids is None or ids.shape == (rows.shape[0],)
+        N.check(N.lib().pkv_index_append(self._h, _np_ptr(rows), _np_ptr(ids), rows.shape[0]))
+
+    def append_blobs(self, blob: bytes, row_ids=None) -> None:
+        """Concatenated SQLite blobs exactly as stored (n * dim * elem_size bytes)."""
+        a = np.frombuffer(blob, dtype=_NP[self.dtype])
+        self.append(a.reshape(-1, self.dim), row_ids)
+
+    def set_scale_artifact(self, artifact: bytes) -> None:
+        buf = (C.c_uint8 * max(len(artifact), 1)).from_buffer_copy(artifact.ljust(1, b"\0"))
+        N.check(N.lib().pkv_index_set_scale(self._h, buf, len(artifact)))
+
+    def set_row_base(self, base: int) -> None:
+        N.check(N.lib().pkv_index_set_row_base(self._h, base))
+
+    def seal(self) -> None:
+        N.check(N.lib().pkv_index_seal(self._h))
+
+    def info(self) -> N.IndexInfo:
+        out = N.IndexInfo()
+        N.check(N.lib().pkv_index_get_info(self._h, C.byref(out)))
+        return out
+
+    def counters(self) -> N.Counters:
+        out = N.Counters()
+        N.check(N.lib().pkv_index_counters(self._h, C.byref(out)))
+        return out
+
+    def set_option(self, name: str, value: int) -> None:
+        N.check(N.lib().pkv_index_set_option(self._h, name.encode(), value))
+
+    @property
+    def rows(self) -> int:
+        return int(self.info().rows)
+
+    # -- search ----------------------------------------------------------------
+    def search(self, queries, k: int, metric: int = N.COSINE, bitmap=None, bitmap_stride_words: int = 0,
+               out=None, stream: int = 0):
+        """Top-k per query under (distance asc, row asc, NaN last).
+
+        NumPy queries -> (ids[nq,k] int64, dist[nq,k] f32, counts[nq] int32) NumPy arrays.
+        torch CUDA queries -> the same as CUDA tensors (device path, no host copies)."""
+        if _is_torch(queries):
+            return self._search_device(queries, k, metric, bitmap, bitmap_stride_words, out, stream)
+        queries = np.ascontiguousarray(queries)
+        if queries.ndim == 1:
+            queries = queries[None, :]
+        qd = _CODE.get(queries.dtype)
+        if qd is None:
+            raise TypeError(f"unsupported query dtype {queries.dtype}")
+        if queries.shape[1] != self.dim:
+            raise N.PkvError(N.ERR_DIM_MISMATCH, f"query dimension {queries.shape[1]} != index dimension {self.dim}")
+        nq = queries.shape[0]
+        p = N.SearchParams(metric=metric, k=k, query_dtype=qd)
+        if bitmap is not None:
+            bitmap = np.ascontiguousarray(bitmap, dtype=np.uint64)
+            p.bitmap = bitmap.ctypes.data
+            p.bitmap_stride_words = bitmap_stride_words
+        kk = max(k, 1)
+        if out is None:
+            ids = np.empty((nq, kk), np.int64)
+            dist = np.empty((nq, kk), np.float32)
+            counts = np.empty(nq, np.int32)
+        else:
+            ids, dist, counts = out
+        N.check(N.lib().pkv_search(self._h, _np_ptr(queries), nq, C.byref(p), _np_ptr(ids), _np_ptr(dist),
+                                   _np_ptr(counts)))
+        return ids, dist, counts
+
+    def _search_device(self, queries, k, metric, bitmap, bitmap_stride_words, out, stream):
+        import torch
+
+        assert queries.is_cuda and queries.is_contiguous() and queries.dim() == 2
+        if queries.shape[1] != self.dim:
+            raise N.PkvError(N.ERR_DIM_MISMATCH, f"query dimension {queries.shape[1]} != index dimension {self.dim}")
+        nq = queries.shape[0]
+        p = N.SearchParams(metric=metric, k=k, query_dtype=_torch_code(queries))
+        if bitmap is not None:
+            assert bitmap.is_cuda and bitmap.dtype in (torch.int64, torch.uint64) and bitmap.is_contiguous()
+            p.bitmap = bitmap.data_ptr()
+            p.bitmap_stride_words = bitmap_stride_words
+        kk = max(k, 1)
+        if out is None:
+            ids = torch.empty((nq, kk), dtype=torch.int64, device=queries.device)
+            dist = torch.empty((nq, kk), dtype=torch.float32, device=queries.device)
+            counts = torch.empty(nq, dtype=torch.int32, device=queries.device)
+        else:
+            ids, dist, counts = out
+        if not stream:
+            stream = torch.cuda.current_stream(queries.device).cuda_stream
+        N.check(N.lib().pkv_search_device(self._h, C.c_void_p(queries.data_ptr()), nq, C.byref(p),
+                                          C.c_void_p(ids.data_ptr()), C.c_void_p(dist.data_ptr()),
+                                          C.c_void_p(counts.data_ptr()), C.c_void_p(stream)))
+        return ids, dist, counts
+
+
+# ---- codec (db/vector_quants.rs:1446-1503) -------------------------------------
+
+def scale_from_absmax(absmax: float) -> float:
+    return float(N.lib().pkv_scale_from_absmax(C.c_float(absmax)))
+
+
+def scale_artifact(scale: float) -> bytes:
+    buf = (C.c_uint8 * 4)()
+    N.lib().pkv_scale_artifact(C.c_float(scale), buf)
+    return bytes(buf)
+
+
+def artifact_scale(artifact: bytes) -> Optional[float]:
+    out = C.c_float()
+    buf = (C.c_uint8 * max(len(artifact), 1)).from_buffer_copy(artifact.ljust(1, b"\0"))
+    st = N.lib().pkv_artifact_scale(buf, len(artifact), C.byref(out))
+    return float(out.value) if st == N.OK else None
+
+
+def blob_absmax(values, device: int = 0) -> float:
+    out = C.c_float()
+    if _is_torch(values):
+        assert values.is_cuda and values.is_contiguous()
+        N.check(N.lib().pkv_blob_absmax_device(device, C.c_void_p(values.data_ptr()), values.numel(), C.byref(out), None))
+    else:
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        N.check(N.lib().pkv_blob_absmax(device, _np_ptr(values), values.size, C.byref(out)))
+    return float(out.value)
+
+
+def quantize_int8(values, scale: float, device: int = 0):
+    """GPU batch codec, bit-exact with the Rust quantize_int8."""
+    if _is_torch(values):
+        import torch
+
+        assert values.is_cuda and values.is_contiguous() and values.dtype == torch.float32
+        codes = torch.empty(values.shape, dtype=torch.int8, device=values.device)
+        N.check(N.lib().pkv_quantize_int8_device(device, C.c_void_p(values.data_ptr()), values.numel(),
+                                                 C.c_float(scale), C.c_void_p(codes.data_ptr()), None))
+        return codes
+    values = np.ascontiguousarray(values, dtype=np.float32)
+    codes = np.empty(values.shape, dtype=np.int8)
+    N.check(N.lib().pkv_quantize_int8(device, _np_ptr(values), values.size, C.c_float(scale), _np_ptr(codes)))
+    return codes
+
+
+def merge_topk(ids, dist, device: int = 0):
+    """ids/dist: torch CUDA tensors [parts, nq, k] as gathered from the row shards."""
+    import torch
+
+    parts, nq, k = ids.shape
+    o_ids = torch.empty((nq, k), dtype=torch.int64, device=ids.device)
+    o_dist = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
+    o_cnt = torch.empty(nq, dtype=torch.int32, device=ids.device)
+    stream = torch.cuda.current_stream(ids.device).cuda_stream
+    N.check(N.lib().pkv_merge_topk_device(device, C.c_void_p(ids.data_ptr()), C.c_void_p(dist.data_ptr()), parts, nq, k,
+                                          C.c_void_p(o_ids.data_ptr()), C.c_void_p(o_dist.data_ptr()),
+                                          C.c_void_p(o_cnt.data_ptr()), C.c_void_p(stream)))
+    return o_ids, o_dist, o_cnt
+
+
+def aggregate(dist, item_of_row, n_items: int, agg: int, weights=None, device: int = 0):
+    """Per-item MIN/MAX/AVG (or weighted mean) of row distances; torch CUDA tensors."""
+    import torch
+
+    out = torch.empty(n_items, dtype=torch.float64, device=dist.device)
+    stream = torch.cuda.current_stream(dist.device).cuda_stream
+    N.check(N.lib().pkv_aggregate_device(device, C.c_void_p(dist.data_ptr()), C.c_void_p(item_of_row.data_ptr()),
+                                         None if weights is None else C.c_void_p(weights.data_ptr()),
+                                         dist.numel(), n_items, agg, C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+    return out

@@ -1,0 +1,71 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+from oracle import oracle as orc
+
+F32_RTOL = 1e-5  # north_star: cosine scores within 1e-5 relative on fp32
+
+
+def assert_exact(got, want):
+    """Bit-exact parity (int8 path): ids, distances (NaN == NaN) and counts."""
+    ids_g, dist_g, cnt_g = got
+    rows_o, dist_o, cnt_o = want
+    assert np.array_equal(np.asarray(cnt_g), cnt_o), (cnt_g, cnt_o)
+    assert np.array_equal(np.asarray(ids_g), rows_o), _first_diff(ids_g, rows_o, dist_g, dist_o)
+    assert np.array_equal(np.asarray(dist_g).view(np.uint32), dist_o.view(np.uint32)), _first_diff(dist_g, dist_o, ids_g, rows_o)
+
+
+def _first_diff(a, b, c, d):
+    a, b = np.asarray(a), np.asarray(b)
+    idx = np.argwhere(a != b)
+    if len(idx) == 0:
+        return "no diff"
+    i = tuple(idx[0])
+    return f"first difference at {i}: got {a[i]} want {b[i]} (aux got {np.asarray(c)[i]} want {np.asarray(d)[i]}); {len(idx)} differing entries"
+
+
+def assert_close_topk(got, want, corpus, queries, metric, rtol=F32_RTOL, atol=1e-7):
+    """f32 parity: the GPU sums in a different order than the scalar loop, so distances agree
+    to `rtol` and ids may differ only where the oracle's own distances are that close."""
+    ids_g, dist_g, cnt_g = (np.asarray(x) for x in got)
+    rows_o, dist_o, cnt_o = want
+    assert np.array_equal(cnt_g, cnt_o), (cnt_g, cnt_o)
+    nq, k = rows_o.shape
+    for q in range(nq):
+        m = cnt_o[q]
+        dg, do = dist_g[q, :m], dist_o[q, :m]
+        nan_g, nan_o = np.isnan(dg), np.isnan(do)
+        assert np.array_equal(nan_g, nan_o), f"query {q}: NaN placement differs"
+        ok = ~nan_o
+        tol = rtol * np.abs(do[ok]) + atol
+        assert np.all(np.abs(dg[ok] - do[ok]) <= tol), (
+            f"query {q}: max rel err {np.max(np.abs(dg[ok]-do[ok])/np.maximum(np.abs(do[ok]),1e-30))}")
+        assert np.all(ids_g[q, m:] == -1)
+        if np.array_equal(ids_g[q, :m], rows_o[q, :m]):
+            continue
+        # every row the GPU returned must carry (to rtol) the distance the oracle gives that row,
+        # and rows only one side returned must sit within rtol of the k-th distance
+        d_rows = orc.distances(corpus[ids_g[q, :m]], queries[q], metric)
+        fin = ~np.isnan(d_rows)
+        assert np.all(np.abs(d_rows[fin] - dg[fin]) <= rtol * np.abs(d_rows[fin]) + atol), f"query {q}: row distance mismatch"
+        kth = do[ok][-1] if ok.any() else 0.0
+        only_g = np.setdiff1d(ids_g[q, :m], rows_o[q, :m])
+        only_o = np.setdiff1d(rows_o[q, :m], ids_g[q, :m])
+        assert len(only_g) == len(only_o)
+        for r in np.concatenate([only_g, only_o]):
+            d = orc.distances(corpus[r:r + 1], queries[q], metric)[0]
+            assert abs(d - kth) <= 2 * (rtol * abs(kth) + atol), f"query {q}: row {r} swapped across a gap {abs(d-kth)}"
+        # rows both sides returned may be permuted only within near-ties
+        pos_o = {r: i for i, r in enumerate(rows_o[q, :m])}
+        for i, r in enumerate(ids_g[q, :m]):
+            j = pos_o.get(r)
+            if j is not None and j != i:
+                assert abs(do[j] - do[i]) <= 2 * (rtol * abs(do[i]) + atol) or (np.isnan(do[j]) and np.isnan(do[i]))
+
+
+def int8_space(n, d, seed=orc.CORPUS_SEED, nq=4):
+    """Synthetic corpus + queries quantised with the corpus' absmax scale."""
+    x = orc.synthetic(n, d, seed)
+    q = orc.synthetic(nq, d, seed + 1)
+    scale = orc.scale_from_absmax(float(np.abs(x).max())) if n else 1.0
+    return x, q, scale, orc.quantize_rows(x, scale), orc.quantize_rows(q, scale)

@@ -1,0 +1,92 @@
+"""CPU-side checks of the C ABI library: it loads, exports every symbol include/pkv.h declares,
+its host-side policy layer mirrors the reference, and compute entry points fail loudly without a GPU."""
+import json
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import panoptikon_b200 as pk
+from panoptikon_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+
+
+def _has_cuda():
+    import torch
+
+    return torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "pkv.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pkv_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = pk.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in pkv.h but not exported"
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    assert lib.pkv_abi_version() == 1
+
+
+def test_host_scalar_codec_matches_reference_kats():
+    g = GOLD["codec"]
+    assert pk.scale_from_absmax(0.0) == 1.0
+    assert pk.scale_from_absmax(float("nan")) == 1.0
+    assert pk.scale_from_absmax(float("inf")) == 1.0
+    assert pk.scale_from_absmax(11.0) == struct.unpack("<f", struct.pack("<f", np.float32(11.0) / np.float32(127.0)))[0]
+    s = pk.scale_from_absmax(g["artifact_roundtrip_absmax"])
+    assert pk.artifact_scale(pk.scale_artifact(s)) == s
+    for hexed in g["artifact_rejects_hex"]:
+        assert pk.artifact_scale(bytes.fromhex(hexed)) is None
+    assert "4 bytes" in N.last_error() or "positive finite" in N.last_error()
+
+
+def test_policy_truth_tables_match_reference():
+    g = GOLD["policy"]
+    for row in g["quant_requested"]:
+        assert pk.quant_requested(pk.parse_index_mode(row["index"]), row["variant"]) == row["expect"], row
+    for row in g["strict"]:
+        assert pk.quant_strict(pk.parse_index_mode(row["index"]), row["variant"]) == row["expect"], row
+    with pytest.raises(pk.PqlError, match=re.escape(g["errors"]["ann"])):
+        pk.validate_quant_args(pk.INDEX_ANN, 10)
+    with pytest.raises(pk.PqlError, match=re.escape(g["errors"]["k"])):
+        pk.validate_quant_args(pk.INDEX_AUTO, 0)
+    pk.validate_quant_args(pk.INDEX_QUANT, 1)
+    assert pk.DEFAULT_K == 10000
+
+
+def test_enum_names_follow_serde():
+    assert [pk.parse_index_mode(n) for n in ("auto", "exact", "quant", "ann")] == [0, 1, 2, 3]
+    with pytest.raises(pk.PqlError):
+        pk.parse_index_mode("Auto")
+    assert pk.parse_distance_function("L2") == pk.L2 and pk.parse_distance_function("COSINE") == pk.COSINE
+    with pytest.raises(pk.PqlError):
+        pk.parse_distance_function("cosine")
+    assert pk.parse_distance_function("CoSiNe", from_override=True) == pk.COSINE  # from_override lowercases
+    assert [pk.parse_distance_aggregation(n) for n in ("MIN", "MAX", "AVG")] == [0, 1, 2]
+
+
+@pytest.mark.skipif(_has_cuda(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    with pytest.raises(pk.PkvError) as e:
+        pk.VectorIndex(8)
+    assert e.value.status == N.ERR_CUDA and "no CPU fallback" in e.value.message
+    with pytest.raises(pk.PkvError):
+        pk.quantize_int8(np.zeros(4, np.float32), 1.0)
+    with pytest.raises(pk.PkvError):
+        pk.blob_absmax(np.zeros(4, np.float32))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "panoptikon_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert not re.search(r"#include\s+[\"<].*oracle", text), f
