@@ -12,7 +12,14 @@ def assert_exact(got, want):
     rows_o, dist_o, cnt_o = want
     assert np.array_equal(np.asarray(cnt_g), cnt_o), (cnt_g, cnt_o)
     assert np.array_equal(np.asarray(ids_g), rows_o), _first_diff(ids_g, rows_o, dist_g, dist_o)
-    assert np.array_equal(np.asarray(dist_g).view(np.uint32), dist_o.view(np.uint32)), _first_diff(dist_g, dist_o, ids_g, rows_o)
+    # bit-exact distances; every NaN (SQL NULL) counts as the same value whatever its sign/payload bits
+    bg, bo = _canon_bits(np.asarray(dist_g)), _canon_bits(dist_o)
+    assert np.array_equal(bg, bo), _first_diff(bg, bo, ids_g, rows_o)
+
+
+def _canon_bits(d):
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    return np.where(np.isnan(d), np.uint32(0x7FC00000), d.view(np.uint32))
 
 
 def _first_diff(a, b, c, d):
