@@ -239,7 +239,7 @@ def np_distances(corpus: np.ndarray, query: np.ndarray, metric: int) -> np.ndarr
                 amag = (amag + (a[:, i] * a[:, i]).astype(f32)).astype(f32)
                 bmag = f32(bmag + f32(q[i] * q[i]))
         if metric == DOT:
-            return (-dot).astype(f32)
+            return (f32(0) - dot).astype(f32)
         den = np.sqrt(amag.astype(np.float64)) * np.sqrt(np.float64(bmag))
         return (1.0 - dot.astype(np.float64) / den).astype(f32)
 

@@ -129,13 +129,13 @@ float orc_distance_l2_i8(const int8_t *a, const int8_t *b, size_t d) {
 float orc_distance_dot_f32(const float *a, const float *b, size_t d) {
     float dot = 0;
     for (size_t i = 0; i < d; i++) dot += a[i] * b[i];
-    return -dot;
+    return 0.0f - dot; /* +0.0 for a zero dot product: equal distances must compare and print alike */
 }
 
 float orc_distance_dot_i8(const int8_t *a, const int8_t *b, size_t d) {
     float dot = 0;
     for (size_t i = 0; i < d; i++) dot += (float)((int)a[i] * (int)b[i]);
-    return -dot;
+    return 0.0f - dot;
 }
 
 float orc_half_to_float(uint16_t h) {

@@ -56,7 +56,7 @@ float orc_distance_cosine_f32(const float *a, const float *b, size_t d);
 float orc_distance_l2_f32(const float *a, const float *b, size_t d);
 float orc_distance_cosine_i8(const int8_t *a, const int8_t *b, size_t d);
 float orc_distance_l2_i8(const int8_t *a, const int8_t *b, size_t d);
-/* benchmark-only metric (BASELINE config 3): distance = -dot */
+/* benchmark-only metric (BASELINE config 3): distance = 0 - dot */
 float orc_distance_dot_f32(const float *a, const float *b, size_t d);
 float orc_distance_dot_i8(const int8_t *a, const int8_t *b, size_t d);
 /* IEEE binary16 bits -> f32 (the fp16 corpus extension widens before scoring) */

@@ -160,6 +160,7 @@ struct SearchRun {
     double scan_ms = 0;
     int launches = 0, scan_launches = 0;
     int depth_overflows = 0;
+    bool use_tc = false;
 };
 
 static int scan_range(SearchRun &r, int64_t b, int64_t e) {
@@ -168,7 +169,10 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e) {
     const bool timed = r.ix.opt.time_kernels != 0;
     if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[0], r.s));
     int n = 0;
-    PKV_TRY(launch_scan_simt(r.ix, r.args, r.s, &n));
+    if (r.use_tc)
+        PKV_TRY(launch_scan_tc(r.ix, r.args, r.s, &n));
+    else
+        PKV_TRY(launch_scan_simt(r.ix, r.args, r.s, &n));
     r.launches += n;
     r.scan_launches += n;
     if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[1], r.s));
@@ -210,6 +214,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     PKV_TRY(launch_reset_state(ws, nq, s));
     SearchRun r{ix, ws, s, ScanArgs{}, filter_spec_simt(ix.dtype, p.metric), nq, k, (int64_t)ws.cap - k};
     r.launches = 2;
+    r.use_tc = scan_tc_supported(ix, nq);
     ScanArgs &a = r.args;
     a.data = ix.d_data;
     a.pitch_bytes = ix.pitch;
@@ -260,7 +265,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     ix.n_scan_launches += r.scan_launches;
     ix.n_fallback += r.depth_overflows;
     ix.last_scan_ms += r.scan_ms;
-    ix.last_scan_kind = ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5);
+    ix.last_scan_kind = r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
     return PKV_OK;
 }
 
@@ -717,6 +722,7 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "first_chunk_rows")) ix.opt.first_chunk_rows = value;
     else if (!strcmp(name, "chunk_growth_x100")) ix.opt.chunk_growth_x100 = value;
     else if (!strcmp(name, "time_kernels")) ix.opt.time_kernels = (int)value;
+    else if (!strcmp(name, "tc_min_queries")) ix.opt.tc_min_queries = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;
 }

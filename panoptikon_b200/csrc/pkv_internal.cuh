@@ -168,6 +168,7 @@ struct Options {
     int64_t first_chunk_rows = 0;    // 0 = auto
     int64_t chunk_growth_x100 = 0;   // 0 = auto
     int time_kernels = 1;
+    int tc_min_queries = 9;          // below this the CUDA-core kernels are HBM-bound anyway
 };
 
 struct Index {
@@ -199,6 +200,9 @@ struct Index {
 // ---- kernels / launchers (each returns a pkv_status) ----
 // pkv_scan_simt.cu
 int launch_scan_simt(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches);
+// pkv_scan_tc.cu (tcgen05 tensor-core path)
+bool scan_tc_supported(const Index &ix, int nq);
+int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches);
 // pkv_topk.cu
 int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);
 int launch_reset_state(Workspace &ws, int nq, cudaStream_t s);

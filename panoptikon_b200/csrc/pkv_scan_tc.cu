@@ -1,0 +1,321 @@
+// pkv_scan_tc.cu — tensor-core scan for int8 rows (tcgen05.mma kind::i8, s32 accumulators in TMEM).
+//
+// Replaces vec_distance_{cosine,L2}(vec_int8(quant), vec_int8(?)) evaluated row by row
+// (pql/builder/filters/image_embeddings.rs:351-362, text_embeddings.rs:407-418) with a dense
+// int8 contraction rows x queries; the integer dot products are exact, the final f32 key is
+// computed with the reference's own operation sequence (pkv_device.cuh: i8_key) for the few
+// pairs that survive the threshold, so top-k ids and distances are bit-exact.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: streams 128-row x 128-byte K-chunks of the corpus into a ring of
+//               SWIZZLE_128B stages (cp.async.bulk.tensor + mbarrier complete_tx)
+//   warp 1      owns TMEM; one elected lane issues tcgen05.mma (M=128 rows, N=128 queries,
+//               K=32 per instruction) against the query tile that stays resident in shared memory,
+//               and tcgen05.commit's stage release / accumulator-ready barriers
+//   warps 2..5  epilogue: tcgen05.ld the 128x128 s32 accumulator (double-buffered in TMEM, so the
+//               next tile's MMAs overlap), integer pre-filter against a per-(warp,query) bound,
+//               exact filter, exact key, candidate push
+//
+// Algorithmic bytes per row per query-tile pass: dim_pad (+4 for the row norm);
+// algorithmic ops: 2 * 128 * dim_pad per row.
+#include "pkv_tc.cuh"
+
+namespace pkv {
+
+namespace {
+
+constexpr int TILE_M = 128;         // corpus rows per MMA
+constexpr int TILE_N = 128;         // queries resident per CTA
+constexpr int CHUNK_BYTES = 128;    // K bytes per stage row (one swizzle atom)
+constexpr int STAGE_BYTES = TILE_M * CHUNK_BYTES;  // 16 KiB
+constexpr int QCHUNK_BYTES = TILE_N * CHUNK_BYTES;
+constexpr int MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 2 * TILE_N;  // double-buffered accumulator
+
+struct TcShared {  // control block behind the data stages
+    uint64_t full[MAX_STAGES];
+    uint64_t empty[MAX_STAGES];
+    uint64_t q_full;
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    float thr[TILE_N];       // per query: filter threshold (metric specific, see below)
+    int q_mag[TILE_N];       // per query: integer squared norm
+    int bound[4][TILE_N];    // per epilogue warp: integer pre-filter bound for the current tile
+};
+
+// Pass decision on the integer dot product d for one (row, query):
+//   COSINE  keep iff  d * rinv >= tneg            (tneg = -thr_f, rinv = 1/sqrt(aMag))
+//   L2      keep iff  aMag + bMag - 2d <= thr_f
+//   DOT     keep iff  -d <= thr_f
+// NaN (zero-norm row) compares false on "<" and is kept, as the SIMT kernel does.
+template <int METRIC>
+__device__ __forceinline__ bool exact_filter(int d, int am, float rinv, int bm, float thr) {
+    if (METRIC == PKV_COSINE) return !((float)d * rinv < -thr);
+    if (METRIC == PKV_L2) return !((float)(am + bm - 2 * d) > thr);
+    return !(-(float)d > thr);
+}
+
+// Integer bound valid for every row of the warp: any pair with d < bound fails exact_filter.
+template <int METRIC>
+__device__ __forceinline__ int prefilter_bound(float thr, int bm, int am_min, int am_max) {
+    const int NONE = -2147483647 - 1;
+    if (!(fabsf(thr) < 3.0e38f)) return thr > 0.f || thr != thr ? NONE : 2147483647;  // +inf/NaN: keep all
+    if (METRIC == PKV_COSINE) {
+        // d >= tneg * sqrt(am); tneg >= 0 -> smallest norm gives the loosest bound, else the largest
+        const float tneg = -thr;
+        const float s = sqrtf((float)(tneg >= 0.f ? am_min : am_max));
+        float b = tneg * s;
+        b = b - fabsf(b) * 1e-6f - 1.0f;  // rounding slack
+        if (b < -2.0e9f) return NONE;
+        if (b > 2.0e9f) return 2147483647;
+        return (int)floorf(b);
+    }
+    if (METRIC == PKV_L2) {
+        // 2d >= am + bm - thr
+        float b = 0.5f * ((float)am_min + (float)bm - thr);
+        b = b - fabsf(b) * 1e-6f - 1.0f;
+        if (b < -2.0e9f) return NONE;
+        if (b > 2.0e9f) return 2147483647;
+        return (int)floorf(b);
+    }
+    float b = -thr;  // d >= -thr
+    b = b - fabsf(b) * 1e-6f - 1.0f;
+    if (b < -2.0e9f) return NONE;
+    if (b > 2.0e9f) return 2147483647;
+    return (int)floorf(b);
+}
+
+template <int METRIC>
+__device__ __forceinline__ void consider(const ScanArgs &a, int q0, int col, int d, uint32_t row, int am, float rinv,
+                                         const TcShared *sh) {
+    const int q = q0 + col;
+    if (q >= a.nq || row >= a.row_end) return;
+    const int bm = sh->q_mag[col];
+    if (!exact_filter<METRIC>(d, am, rinv, bm, sh->thr[col])) return;
+    if (!topk_member(a.topk, q, row)) return;
+    const int8_t *rowp = (const int8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
+    const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
+    topk_push(a.topk, q, row, i8_key(METRIC, d, am, bm, a.dim, rowp, qp));
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
+                  const ScanArgs a, const int q0, const int kchunks, const int stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = tc::smem_u32(smem_raw);
+    uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024-B alignment
+    uint8_t *s_q = smem;                                    // [kchunks][128 queries][128 B]
+    uint8_t *s_a = smem + (size_t)kchunks * QCHUNK_BYTES;   // [stages][128 rows][128 B]
+    TcShared *sh = reinterpret_cast<TcShared *>(s_a + (size_t)stages * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nrows = a.row_end - a.row_begin;
+    const uint32_t ntiles = (nrows + TILE_M - 1) / TILE_M;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            tc::mbar_init(&sh->full[s], 1);
+            tc::mbar_init(&sh->empty[s], 1);
+        }
+        tc::mbar_init(&sh->q_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&sh->tmem_full[b], 1);
+            tc::mbar_init(&sh->tmem_empty[b], 4);
+        }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmap_rows);
+        tc::prefetch_tmap(&tmap_q);
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(&sh->tmem_base, TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    if (warp >= 2) {
+        const int col = threadIdx.x - 64;  // 0..127
+        const int q = q0 + col;
+        sh->thr[col] = q < a.nq ? __ldg(a.topk.thr_f + q) : -__int_as_float(0x7f800000);
+        sh->q_mag[col] = q < a.nq ? __ldg(a.q_mag_i + q) : 0;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tc::mbar_expect_tx(&sh->q_full, (uint32_t)kchunks * QCHUNK_BYTES);
+            for (int kc = 0; kc < kchunks; ++kc)
+                tc::tma_load_2d(s_q + (size_t)kc * QCHUNK_BYTES, &tmap_q, &sh->q_full, kc * CHUNK_BYTES, q0);
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int row0 = (int)(a.row_begin + tile * TILE_M);
+                for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                    tc::mbar_wait(&sh->empty[s], ph ^ 1);
+                    tc::mbar_expect_tx(&sh->full[s], STAGE_BYTES);
+                    tc::tma_load_2d(s_a + (size_t)s * STAGE_BYTES, &tmap_rows, &sh->full[s], kc * CHUNK_BYTES, row0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, TILE_M, TILE_N);
+            tc::mbar_wait(&sh->q_full, 0);
+            tc::fence_after_sync();
+            uint32_t it = 0, t = 0;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+                const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+                tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * TILE_N;
+                for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                    tc::mbar_wait(&sh->full[s], ph);
+                    tc::fence_after_sync();
+                    const uint32_t a_addr = tc::smem_u32(s_a + (size_t)s * STAGE_BYTES);
+                    const uint32_t b_addr = tc::smem_u32(s_q + (size_t)kc * QCHUNK_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
+                        tc::mma_i8(d_tmem, tc::smem_desc_sw128(a_addr + k * 32), tc::smem_desc_sw128(b_addr + k * 32),
+                                   idesc, (kc | k) != 0);
+                    }
+                    tc::mma_commit(&sh->empty[s]);  // stage free once these MMAs have read it
+                }
+                tc::mma_commit(&sh->tmem_full[buf]);  // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int ew = warp - 2;         // private bound[] slot
+        const int quarter = warp & 3;    // TMEM lane quarter this warp may access
+        uint32_t t = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+            const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            const uint32_t row = a.row_begin + tile * TILE_M + quarter * 32 + lane;
+            const bool row_ok = row < a.row_end;
+            const int am = row_ok ? __ldg(a.row_mag_i + row) : 0;
+            const float rinv = rsqrtf((float)am);
+            // rows past the end must not loosen the warp's bound
+            const int am_min = __reduce_min_sync(0xffffffffu, row_ok ? am : 2147483647);
+            const int am_max = __reduce_max_sync(0xffffffffu, am);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < TILE_N / 32; ++i) {
+                const int col = i * 32 + lane;
+                sh->bound[ew][col] = prefilter_bound<METRIC>(sh->thr[col], sh->q_mag[col], am_min, am_max);
+            }
+            __syncwarp();
+            tc::mbar_wait(&sh->tmem_full[buf], bph);
+            tc::fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TILE_N;
+#pragma unroll 1
+            for (int c = 0; c < TILE_N / 32; ++c) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(taddr + c * 32, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int4 b = *reinterpret_cast<const int4 *>(&sh->bound[ew][c * 32 + j]);
+                    const int d0 = (int)v[j], d1 = (int)v[j + 1], d2 = (int)v[j + 2], d3 = (int)v[j + 3];
+                    if ((d0 >= b.x) | (d1 >= b.y) | (d2 >= b.z) | (d3 >= b.w)) {
+                        if (d0 >= b.x) consider<METRIC>(a, q0, c * 32 + j, d0, row, am, rinv, sh);
+                        if (d1 >= b.y) consider<METRIC>(a, q0, c * 32 + j + 1, d1, row, am, rinv, sh);
+                        if (d2 >= b.z) consider<METRIC>(a, q0, c * 32 + j + 2, d2, row, am, rinv, sh);
+                        if (d3 >= b.w) consider<METRIC>(a, q0, c * 32 + j + 3, d3, row, am, rinv, sh);
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+        }
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        // resolved at run time so that libpkv.so carries no link-time dependency on libcuda.so
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// 2-D map over a row-major [rows][inner_bytes] byte matrix, box = 128 B x box_rows, SWIZZLE_128B
+int make_map(CUtensorMap *m, const void *base, uint64_t inner_bytes, uint64_t rows, uint64_t pitch_bytes,
+             uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(PKV_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
+    cuuint64_t dims[2] = {inner_bytes, rows};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {CHUNK_BYTES, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PKV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return PKV_OK;
+}
+
+template <int METRIC>
+int launch_metric(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, const CUtensorMap &mq, int q0,
+                  int kchunks, int stages, size_t smem, cudaStream_t s) {
+    auto kernel = scan_i8_tc_kernel<METRIC>;
+    PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t ntiles = (a.row_end - a.row_begin + TILE_M - 1) / TILE_M;
+    const unsigned grid = ntiles < (uint32_t)ix.sm_count ? ntiles : (unsigned)ix.sm_count;
+    kernel<<<grid, TC_THREADS, smem, s>>>(mrows, mq, a, q0, kchunks, stages);
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
+}  // namespace
+
+bool scan_tc_supported(const Index &ix, int nq) {
+    if (ix.dtype != PKV_I8 || ix.opt.force_simt) return false;
+    if (ix.dim_pad > 1024) return false;  // the resident query tile must leave room for >= 4 stages
+    return nq >= ix.opt.tc_min_queries;
+}
+
+int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches) {
+    if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
+    const int kchunks = ix.dim_pad / CHUNK_BYTES;
+    const size_t ctrl = sizeof(TcShared);
+    int stages = (int)((227 * 1024 - 1024 - ctrl - (size_t)kchunks * QCHUNK_BYTES) / STAGE_BYTES);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return fail(PKV_ERR_UNSUPPORTED, "dim %d leaves no room for the row stages", ix.dim);
+    const size_t smem = 1024 + (size_t)kchunks * QCHUNK_BYTES + (size_t)stages * STAGE_BYTES + ctrl;
+    CUtensorMap mrows, mq;
+    PKV_TRY(make_map(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
+    PKV_TRY(make_map(&mq, a.queries, (uint64_t)ix.dim_pad, (uint64_t)a.nq, (uint64_t)ix.dim_pad, TILE_N));
+    for (int q0 = 0; q0 < a.nq; q0 += TILE_N) {
+        *launches += 1;
+        switch (a.metric) {
+            case PKV_COSINE: PKV_TRY(launch_metric<PKV_COSINE>(ix, a, mrows, mq, q0, kchunks, stages, smem, s)); break;
+            case PKV_L2: PKV_TRY(launch_metric<PKV_L2>(ix, a, mrows, mq, q0, kchunks, stages, smem, s)); break;
+            default: PKV_TRY(launch_metric<PKV_DOT>(ix, a, mrows, mq, q0, kchunks, stages, smem, s)); break;
+        }
+    }
+    return PKV_OK;
+}
+
+}  // namespace pkv

@@ -1,0 +1,80 @@
+"""Tensor-core (tcgen05 kind::i8) scan against the oracle: bit-exact ids and distances, and
+identical to the CUDA-core kernel on the same index."""
+import numpy as np
+import pytest
+
+import panoptikon_b200 as pk
+from oracle import oracle as orc
+from tests.helpers import assert_exact, int8_space
+
+pytestmark = pytest.mark.gpu
+METRICS = [pk.L2, pk.COSINE, pk.DOT]
+
+
+def _index(xc, scale=None):
+    ix = pk.VectorIndex(xc.shape[1], pk.I8)
+    if scale is not None:
+        ix.set_scale_artifact(pk.scale_artifact(scale))
+    ix.append(xc)
+    ix.seal()
+    return ix
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("nq", [9, 128, 130])
+def test_tc_int8_bit_exact(metric, nq):
+    x, q, scale, xc, qc = int8_space(70001, 768, 101, nq)
+    with _index(xc, scale) as ix:
+        got = ix.search(qc, 100, metric)
+        assert ix.counters().last_scan_kind == 3, "tensor-core kernel did not run"
+        ix.set_option("force_simt", 1)
+        simt = ix.search(qc, 100, metric)
+        assert ix.counters().last_scan_kind == 2
+    want = orc.topk(xc, qc, metric, 100, threads=16)
+    assert_exact(got, want)
+    assert_exact(simt, want)
+
+
+@pytest.mark.parametrize("dim", [8, 128, 520, 1024])
+def test_tc_dims_saturation_zero_rows(dim):
+    rng = np.random.default_rng(7)
+    xc = rng.integers(-128, 128, size=(3000, dim), dtype=np.int8)
+    xc[7] = -128
+    xc[8] = 127
+    xc[9] = 0
+    xc[2999] = 0
+    qc = rng.integers(-128, 128, size=(20, dim), dtype=np.int8)
+    qc[0] = -128
+    qc[1] = 0   # zero query: every cosine is NaN
+    with _index(xc) as ix:
+        for metric in METRICS:
+            k = 3000 if dim == 8 else 77
+            got = ix.search(qc, k, metric)
+            assert ix.counters().last_scan_kind == 3
+            assert_exact(got, orc.topk(xc, qc, metric, k, threads=8))
+
+
+def test_tc_bitmap_duplicates_and_overflow():
+    base = np.random.default_rng(8).integers(-100, 100, size=(7, 256), dtype=np.int8)
+    xc = np.ascontiguousarray(np.tile(base, (6000, 1)))
+    qc = np.ascontiguousarray(np.tile(base, (3, 1))[:16])
+    rng = np.random.default_rng(9)
+    words = (len(xc) + 63) // 64
+    shared = np.packbits(rng.random(words * 64) < 0.3, bitorder="little").view(np.uint64)
+    with _index(xc) as ix:
+        assert_exact(ix.search(qc, 500, pk.COSINE), orc.topk(xc, qc, orc.COSINE, 500, threads=8))
+        assert_exact(ix.search(qc, 200, pk.L2, bitmap=shared), orc.topk(xc, qc, orc.L2, 200, bitmap=shared, threads=8))
+        ix.set_option("candidate_capacity", 256)   # force range splitting
+        assert_exact(ix.search(qc, 100, pk.COSINE), orc.topk(xc, qc, orc.COSINE, 100, threads=8))
+        assert ix.counters().last_scan_kind == 3
+
+
+def test_tc_adversarial_order():
+    x, q, scale, xc, qc = int8_space(50000, 128, 111, 12)
+    order = np.argsort(xc.astype(np.int32) @ qc[0].astype(np.int32))   # ascending similarity to query 0
+    xc = np.ascontiguousarray(xc[order])
+    with _index(xc, scale) as ix:
+        ix.set_option("candidate_capacity", 512)
+        got = ix.search(qc, 50, pk.COSINE)
+        assert ix.counters().fallback_queries > 0
+    assert_exact(got, orc.topk(xc, qc, orc.COSINE, 50, threads=8))
