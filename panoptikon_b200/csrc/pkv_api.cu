@@ -60,6 +60,8 @@ Workspace::~Workspace() {
     cudaFree(d_thr_key);
     cudaFree(d_thr_f);
     cudaFree(d_status);
+    cudaFree(d_pend_rows);
+    cudaFree(d_pend_cnt);
     if (h_status) cudaFreeHost(h_status);
     cudaFree(d_out_ids);
     cudaFree(d_out_dist);
@@ -125,6 +127,10 @@ static int make_workspace(Index &ix, int nq, int k, size_t out_rows, Workspace *
         A((void **)&ws->d_thr_key, sizeof(uint64_t) * nq_cap);
         A((void **)&ws->d_thr_f, sizeof(float) * nq_cap);
         A((void **)&ws->d_status, sizeof(SearchStatus));
+        if (ix.dtype == PKV_F32) {
+            A((void **)&ws->d_pend_rows, sizeof(uint32_t) * (size_t)nq_cap * cap);
+            A((void **)&ws->d_pend_cnt, sizeof(uint32_t) * nq_cap);
+        }
         A((void **)&ws->d_out_ids, sizeof(int64_t) * out_rows);
         A((void **)&ws->d_out_dist, sizeof(float) * out_rows);
         A((void **)&ws->d_out_counts, sizeof(int32_t) * (out_rows ? out_rows : 1));
@@ -160,7 +166,7 @@ struct SearchRun {
     double scan_ms = 0;
     int launches = 0, scan_launches = 0;
     int depth_overflows = 0;
-    bool use_tc = false;
+    bool use_tc = false, use_tc_f32 = false;
 };
 
 static int scan_range(SearchRun &r, int64_t b, int64_t e) {
@@ -169,7 +175,11 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e) {
     const bool timed = r.ix.opt.time_kernels != 0;
     if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[0], r.s));
     int n = 0;
-    if (r.use_tc)
+    PKV_TRY(launch_reset_status(r.ws, r.s));
+    if (r.use_tc_f32)
+        PKV_TRY(launch_scan_tc_f32(r.ix, r.args, r.ws.d_pend_rows, r.ws.d_pend_cnt, (uint32_t)r.ws.cap, r.ws.d_status,
+                                   r.s, &n));
+    else if (r.use_tc)
         PKV_TRY(launch_scan_tc(r.ix, r.args, r.s, &n));
     else
         PKV_TRY(launch_scan_simt(r.ix, r.args, r.s, &n));
@@ -215,6 +225,8 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     SearchRun r{ix, ws, s, ScanArgs{}, filter_spec_simt(ix.dtype, p.metric), nq, k, (int64_t)ws.cap - k};
     r.launches = 2;
     r.use_tc = scan_tc_supported(ix, nq);
+    r.use_tc_f32 = scan_tc_f32_supported(ix, nq);
+    if (r.use_tc_f32) r.fs = filter_spec_tc_f32(p.metric);
     ScanArgs &a = r.args;
     a.data = ix.d_data;
     a.pitch_bytes = ix.pitch;
@@ -265,7 +277,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     ix.n_scan_launches += r.scan_launches;
     ix.n_fallback += r.depth_overflows;
     ix.last_scan_ms += r.scan_ms;
-    ix.last_scan_kind = r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
+    ix.last_scan_kind = r.use_tc_f32 ? 4 : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
     return PKV_OK;
 }
 
@@ -723,6 +735,7 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "chunk_growth_x100")) ix.opt.chunk_growth_x100 = value;
     else if (!strcmp(name, "time_kernels")) ix.opt.time_kernels = (int)value;
     else if (!strcmp(name, "tc_min_queries")) ix.opt.tc_min_queries = (int)value;
+    else if (!strcmp(name, "tc_min_queries_f32")) ix.opt.tc_min_queries_f32 = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;
 }

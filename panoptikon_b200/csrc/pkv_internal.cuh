@@ -150,6 +150,8 @@ struct Workspace {
     uint32_t *d_cnt = nullptr;
     uint64_t *d_thr_key = nullptr;
     float *d_thr_f = nullptr;
+    uint32_t *d_pend_rows = nullptr;  // tf32 path: rows awaiting exact re-scoring, [nq_cap][cap]
+    uint32_t *d_pend_cnt = nullptr;
     SearchStatus *d_status = nullptr;
     SearchStatus *h_status = nullptr;  // pinned
     int64_t *d_out_ids = nullptr;
@@ -168,6 +170,7 @@ struct Options {
     int64_t first_chunk_rows = 0;    // 0 = auto
     int64_t chunk_growth_x100 = 0;   // 0 = auto
     int time_kernels = 1;
+    int tc_min_queries_f32 = 17;     // f32: the FFMA kernel is HBM-bound up to ~16 queries
     int tc_min_queries = 9;          // below this the CUDA-core kernels are HBM-bound anyway
 };
 
@@ -203,7 +206,13 @@ int launch_scan_simt(const Index &ix, const ScanArgs &a, cudaStream_t s, int *la
 // pkv_scan_tc.cu (tcgen05 tensor-core path)
 bool scan_tc_supported(const Index &ix, int nq);
 int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches);
+// pkv_scan_tc_f32.cu (tf32 filter + exact re-scoring)
+bool scan_tc_f32_supported(const Index &ix, int nq);
+FilterSpec filter_spec_tc_f32(int metric);
+int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, uint32_t *d_pend_rows, uint32_t *d_pend_cnt,
+                       uint32_t pend_cap, SearchStatus *d_status, cudaStream_t s, int *launches);
 // pkv_topk.cu
+int launch_reset_status(Workspace &ws, cudaStream_t s);
 int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);
 int launch_reset_state(Workspace &ws, int nq, cudaStream_t s);
 int launch_select(const Index &ix, Workspace &ws, int nq, int k, int metric, FilterSpec fs, cudaStream_t s);

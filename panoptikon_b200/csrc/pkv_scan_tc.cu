@@ -30,8 +30,14 @@ constexpr int CHUNK_BYTES = 128;    // K bytes per stage row (one swizzle atom)
 constexpr int STAGE_BYTES = TILE_M * CHUNK_BYTES;  // 16 KiB
 constexpr int QCHUNK_BYTES = TILE_N * CHUNK_BYTES;
 constexpr int MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;        // two warps per TMEM lane quarter, 64 columns each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 2 * TILE_N;  // double-buffered accumulator
+constexpr int COLS_PER_WARP = TILE_N / 2;
+constexpr int HOLD_CAP = 1536;      // staged pre-filter survivors per CTA
+constexpr int FLUSH_EVERY = 4;      // tiles between cooperative flushes
+constexpr int BOUND_LIM = 1 << 30;
 
 struct TcShared {  // control block behind the data stages
     uint64_t full[MAX_STAGES];
@@ -40,65 +46,93 @@ struct TcShared {  // control block behind the data stages
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
-    uint32_t pad;
-    float thr[TILE_N];       // per query: filter threshold (metric specific, see below)
+    uint32_t hold_cnt;
+    alignas(16) float thr[TILE_N];  // per query: filter threshold thr_f (metric specific)
+    float tq[TILE_N];        // per query: finite, clamped figure the integer bound is derived from
     int q_mag[TILE_N];       // per query: integer squared norm
-    int bound[4][TILE_N];    // per epilogue warp: integer pre-filter bound for the current tile
+    alignas(16) int bound[EPI_WARPS][COLS_PER_WARP];  // per epilogue warp: integer pre-filter bound, current tile
+    uint32_t hold_row[HOLD_CAP];          // pre-filter survivors waiting for the lane-parallel flush
+    int hold_dot[HOLD_CAP];
+    uint32_t hold_col[HOLD_CAP];
 };
 
 // Pass decision on the integer dot product d for one (row, query):
-//   COSINE  keep iff  d * rinv >= tneg            (tneg = -thr_f, rinv = 1/sqrt(aMag))
+//   COSINE  keep iff  d * rinv >= -thr_f          (rinv = 1/sqrt(aMag))
 //   L2      keep iff  aMag + bMag - 2d <= thr_f
 //   DOT     keep iff  -d <= thr_f
-// NaN (zero-norm row) compares false on "<" and is kept, as the SIMT kernel does.
+// NaN (zero-norm row) compares false and is kept, as the SIMT kernel does.
 template <int METRIC>
-__device__ __forceinline__ bool exact_filter(int d, int am, float rinv, int bm, float thr) {
-    if (METRIC == PKV_COSINE) return !((float)d * rinv < -thr);
+__device__ __forceinline__ bool exact_filter(int d, int am, int bm, float thr) {
+    if (METRIC == PKV_COSINE) return !((float)d * rsqrtf((float)am) < -thr);
     if (METRIC == PKV_L2) return !((float)(am + bm - 2 * d) > thr);
     return !(-(float)d > thr);
 }
 
-// Integer bound valid for every row of the warp: any pair with d < bound fails exact_filter.
+// Per-query figure for the integer pre-filter (computed once per kernel):
+//   COSINE: tneg = -thr_f              bound = tneg * sqrt(am)
+//   L2    : c    = bMag - thr_f        bound = (am + c) / 2
+//   DOT   : tneg = -thr_f              bound = tneg
+// +inf threshold ("keep everything") becomes -1e30, -inf ("keep nothing") +1e30.
 template <int METRIC>
-__device__ __forceinline__ int prefilter_bound(float thr, int bm, int am_min, int am_max) {
-    const int NONE = -2147483647 - 1;
-    if (!(fabsf(thr) < 3.0e38f)) return thr > 0.f || thr != thr ? NONE : 2147483647;  // +inf/NaN: keep all
-    if (METRIC == PKV_COSINE) {
-        // d >= tneg * sqrt(am); tneg >= 0 -> smallest norm gives the loosest bound, else the largest
-        const float tneg = -thr;
-        const float s = sqrtf((float)(tneg >= 0.f ? am_min : am_max));
-        float b = tneg * s;
-        b = b - fabsf(b) * 1e-6f - 1.0f;  // rounding slack
-        if (b < -2.0e9f) return NONE;
-        if (b > 2.0e9f) return 2147483647;
-        return (int)floorf(b);
-    }
-    if (METRIC == PKV_L2) {
-        // 2d >= am + bm - thr
-        float b = 0.5f * ((float)am_min + (float)bm - thr);
-        b = b - fabsf(b) * 1e-6f - 1.0f;
-        if (b < -2.0e9f) return NONE;
-        if (b > 2.0e9f) return 2147483647;
-        return (int)floorf(b);
-    }
-    float b = -thr;  // d >= -thr
-    b = b - fabsf(b) * 1e-6f - 1.0f;
-    if (b < -2.0e9f) return NONE;
-    if (b > 2.0e9f) return 2147483647;
-    return (int)floorf(b);
+__device__ __forceinline__ float prefilter_query_figure(float thr, int bm) {
+    float t = METRIC == PKV_L2 ? (float)bm - thr : -thr;
+    if (t != t) t = -1e30f;
+    return fminf(fmaxf(t, -1e30f), 1e30f);
+}
+// Integer bound valid for every row of the warp: a pair with d < bound fails exact_filter.
+template <int METRIC>
+__device__ __forceinline__ int prefilter_bound(float tq, float s_min, float s_max, float am_min_f) {
+    float b;
+    if (METRIC == PKV_COSINE)
+        b = tq * (tq >= 0.f ? s_min : s_max);  // loosest norm in the warp
+    else if (METRIC == PKV_L2)
+        b = 0.5f * (am_min_f + tq);
+    else
+        b = tq;
+    b = b - fabsf(b) * 2e-6f - 1.0f;  // rounding slack, floor
+    b = fminf(fmaxf(b, -(float)BOUND_LIM), (float)BOUND_LIM);
+    return __float2int_rd(b);
 }
 
+// Exact filter, exact key, candidate push for one pre-filter survivor.
 template <int METRIC>
-__device__ __forceinline__ void consider(const ScanArgs &a, int q0, int col, int d, uint32_t row, int am, float rinv,
-                                         const TcShared *sh) {
+__device__ __noinline__ void consider(const ScanArgs &a, int q0, int col, int d, uint32_t row, const TcShared *sh) {
     const int q = q0 + col;
     if (q >= a.nq || row >= a.row_end) return;
+    const int am = __ldg(a.row_mag_i + row);
     const int bm = sh->q_mag[col];
-    if (!exact_filter<METRIC>(d, am, rinv, bm, sh->thr[col])) return;
+    if (!exact_filter<METRIC>(d, am, bm, sh->thr[col])) return;
     if (!topk_member(a.topk, q, row)) return;
     const int8_t *rowp = (const int8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
     const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
     topk_push(a.topk, q, row, i8_key(METRIC, d, am, bm, a.dim, rowp, qp));
+}
+
+// A lane found a survivor: park it in shared memory (cheap) so that the expensive part runs
+// later with 32 survivors per warp in flight instead of one.
+template <int METRIC>
+__device__ __noinline__ void hold(const ScanArgs &a, int q0, int col, int d, uint32_t row, TcShared *sh) {
+    const uint32_t slot = atomicAdd(&sh->hold_cnt, 1u);
+    if (slot < HOLD_CAP) {
+        sh->hold_row[slot] = row;
+        sh->hold_dot[slot] = d;
+        sh->hold_col[slot] = (uint32_t)col;
+    } else {
+        consider<METRIC>(a, q0, col, d, row, sh);  // buffer full (unthresholded first chunk): do it now
+    }
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+template <int METRIC>
+__device__ __forceinline__ void flush_held(const ScanArgs &a, int q0, TcShared *sh, int epi_tid) {
+    epi_barrier();
+    const uint32_t n = sh->hold_cnt < HOLD_CAP ? sh->hold_cnt : HOLD_CAP;
+    for (uint32_t e = epi_tid; e < n; e += EPI_THREADS)
+        consider<METRIC>(a, q0, (int)sh->hold_col[e], sh->hold_dot[e], sh->hold_row[e], sh);
+    epi_barrier();
+    if (epi_tid == 0) sh->hold_cnt = 0;
+    epi_barrier();
 }
 
 template <int METRIC>
@@ -124,8 +158,9 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         tc::mbar_init(&sh->q_full, 1);
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&sh->tmem_full[b], 1);
-            tc::mbar_init(&sh->tmem_empty[b], 4);
+            tc::mbar_init(&sh->tmem_empty[b], EPI_WARPS);
         }
+        sh->hold_cnt = 0;
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_rows);
         tc::prefetch_tmap(&tmap_q);
@@ -135,10 +170,15 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         tc::tmem_relinquish();
     }
     if (warp >= 2) {
-        const int col = threadIdx.x - 64;  // 0..127
-        const int q = q0 + col;
-        sh->thr[col] = q < a.nq ? __ldg(a.topk.thr_f + q) : -__int_as_float(0x7f800000);
-        sh->q_mag[col] = q < a.nq ? __ldg(a.q_mag_i + q) : 0;
+        const int col = threadIdx.x - 64;
+        if (col < TILE_N) {
+            const int q = q0 + col;
+            const float thr = q < a.nq ? __ldg(a.topk.thr_f + q) : -__int_as_float(0x7f800000);
+            const int bm = q < a.nq ? __ldg(a.q_mag_i + q) : 0;
+            sh->thr[col] = thr;
+            sh->q_mag[col] = bm;
+            sh->tq[col] = prefilter_query_figure<METRIC>(thr, bm);
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -151,14 +191,14 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             tc::mbar_expect_tx(&sh->q_full, (uint32_t)kchunks * QCHUNK_BYTES);
             for (int kc = 0; kc < kchunks; ++kc)
                 tc::tma_load_2d(s_q + (size_t)kc * QCHUNK_BYTES, &tmap_q, &sh->q_full, kc * CHUNK_BYTES, q0);
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = (int)(a.row_begin + tile * TILE_M);
-                for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->empty[s], ph ^ 1);
                     tc::mbar_expect_tx(&sh->full[s], STAGE_BYTES);
                     tc::tma_load_2d(s_a + (size_t)s * STAGE_BYTES, &tmap_rows, &sh->full[s], kc * CHUNK_BYTES, row0);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -168,14 +208,13 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, TILE_M, TILE_N);
             tc::mbar_wait(&sh->q_full, 0);
             tc::fence_after_sync();
-            uint32_t it = 0, t = 0;
+            uint32_t s = 0, ph = 0, t = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
                 const uint32_t buf = t & 1, bph = (t >> 1) & 1;
                 tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
                 tc::fence_after_sync();
                 const uint32_t d_tmem = tmem_base + buf * TILE_N;
-                for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
                     const uint32_t a_addr = tc::smem_u32(s_a + (size_t)s * STAGE_BYTES);
@@ -186,55 +225,67 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
                                    idesc, (kc | k) != 0);
                     }
                     tc::mma_commit(&sh->empty[s]);  // stage free once these MMAs have read it
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
                 tc::mma_commit(&sh->tmem_full[buf]);  // accumulator complete
             }
         }
     } else {
         // ===================== epilogue =====================
-        const int ew = warp - 2;         // private bound[] slot
-        const int quarter = warp & 3;    // TMEM lane quarter this warp may access
+        const int ew = warp - 2;           // 0..7
+        const int epi_tid = threadIdx.x - 64;
+        const int quarter = warp & 3;      // TMEM lane quarter this warp may access
+        const int half = ew >> 2;          // which 64 columns
+        const int col0 = half * COLS_PER_WARP;
         uint32_t t = 0;
+        uint32_t row = a.row_begin + blockIdx.x * TILE_M + quarter * 32 + lane;
+        int am = (blockIdx.x < ntiles && row < a.row_end) ? __ldg(a.row_mag_i + row) : -1;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
             const uint32_t buf = t & 1, bph = (t >> 1) & 1;
-            const uint32_t row = a.row_begin + tile * TILE_M + quarter * 32 + lane;
-            const bool row_ok = row < a.row_end;
-            const int am = row_ok ? __ldg(a.row_mag_i + row) : 0;
-            const float rinv = rsqrtf((float)am);
-            // rows past the end must not loosen the warp's bound
+            const uint32_t cur_row = row;
+            const bool row_ok = am >= 0;
+            // rows past the end must not loosen (min) the warp's bound
             const int am_min = __reduce_min_sync(0xffffffffu, row_ok ? am : 2147483647);
-            const int am_max = __reduce_max_sync(0xffffffffu, am);
-            __syncwarp();
+            const int am_max = __reduce_max_sync(0xffffffffu, row_ok ? am : 0);
+            // prefetch the next tile's row norm behind this tile's work
+            row = a.row_begin + (tile + gridDim.x) * TILE_M + quarter * 32 + lane;
+            am = (tile + gridDim.x < ntiles && row < a.row_end) ? __ldg(a.row_mag_i + row) : -1;
+            const float s_min = sqrtf((float)am_min), s_max = sqrtf((float)am_max), am_min_f = (float)am_min;
 #pragma unroll
-            for (int i = 0; i < TILE_N / 32; ++i) {
-                const int col = i * 32 + lane;
-                sh->bound[ew][col] = prefilter_bound<METRIC>(sh->thr[col], sh->q_mag[col], am_min, am_max);
+            for (int i = 0; i < COLS_PER_WARP / 32; ++i) {
+                const int c = i * 32 + lane;
+                sh->bound[ew][c] = prefilter_bound<METRIC>(sh->tq[col0 + c], s_min, s_max, am_min_f);
             }
             __syncwarp();
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TILE_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TILE_N + col0;
 #pragma unroll 1
-            for (int c = 0; c < TILE_N / 32; ++c) {
+            for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
                 uint32_t v[32];
                 tc::tmem_ld_32x32(taddr + c * 32, v);
                 tc::tmem_ld_wait();
+                // sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once
+                int any = 0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int4 b = *reinterpret_cast<const int4 *>(&sh->bound[ew][c * 32 + j]);
-                    const int d0 = (int)v[j], d1 = (int)v[j + 1], d2 = (int)v[j + 2], d3 = (int)v[j + 3];
-                    if ((d0 >= b.x) | (d1 >= b.y) | (d2 >= b.z) | (d3 >= b.w)) {
-                        if (d0 >= b.x) consider<METRIC>(a, q0, c * 32 + j, d0, row, am, rinv, sh);
-                        if (d1 >= b.y) consider<METRIC>(a, q0, c * 32 + j + 1, d1, row, am, rinv, sh);
-                        if (d2 >= b.z) consider<METRIC>(a, q0, c * 32 + j + 2, d2, row, am, rinv, sh);
-                        if (d3 >= b.w) consider<METRIC>(a, q0, c * 32 + j + 3, d3, row, am, rinv, sh);
+                    any |= (b.x + ~(int)v[j]) | (b.y + ~(int)v[j + 1]) | (b.z + ~(int)v[j + 2]) | (b.w + ~(int)v[j + 3]);
+                }
+                if (any < 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int d = (int)v[j];
+                        if (d >= sh->bound[ew][c * 32 + j]) hold<METRIC>(a, q0, col0 + c * 32 + j, d, cur_row, sh);
                     }
                 }
             }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+            if ((t % FLUSH_EVERY) == FLUSH_EVERY - 1) flush_held<METRIC>(a, q0, sh, epi_tid);
         }
+        flush_held<METRIC>(a, q0, sh, epi_tid);
     }
 
     tc::fence_before_sync();
@@ -260,9 +311,11 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+}  // namespace
+
 // 2-D map over a row-major [rows][inner_bytes] byte matrix, box = 128 B x box_rows, SWIZZLE_128B
-int make_map(CUtensorMap *m, const void *base, uint64_t inner_bytes, uint64_t rows, uint64_t pitch_bytes,
-             uint32_t box_rows) {
+int make_tmap_bytes(CUtensorMap *m, const void *base, uint64_t inner_bytes, uint64_t rows, uint64_t pitch_bytes,
+                    uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(PKV_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
     cuuint64_t dims[2] = {inner_bytes, rows};
@@ -270,11 +323,13 @@ int make_map(CUtensorMap *m, const void *base, uint64_t inner_bytes, uint64_t ro
     cuuint32_t box[2] = {CHUNK_BYTES, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PKV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return PKV_OK;
 }
+
+namespace {
 
 template <int METRIC>
 int launch_metric(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, const CUtensorMap &mq, int q0,
@@ -305,8 +360,8 @@ int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *laun
     if (stages < 2) return fail(PKV_ERR_UNSUPPORTED, "dim %d leaves no room for the row stages", ix.dim);
     const size_t smem = 1024 + (size_t)kchunks * QCHUNK_BYTES + (size_t)stages * STAGE_BYTES + ctrl;
     CUtensorMap mrows, mq;
-    PKV_TRY(make_map(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
-    PKV_TRY(make_map(&mq, a.queries, (uint64_t)ix.dim_pad, (uint64_t)a.nq, (uint64_t)ix.dim_pad, TILE_N));
+    PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
+    PKV_TRY(make_tmap_bytes(&mq, a.queries, (uint64_t)ix.dim_pad, (uint64_t)a.nq, (uint64_t)ix.dim_pad, TILE_N));
     for (int q0 = 0; q0 < a.nq; q0 += TILE_N) {
         *launches += 1;
         switch (a.metric) {

@@ -402,13 +402,18 @@ int launch_reset_state(Workspace &ws, int nq, cudaStream_t s) {
     return PKV_OK;
 }
 
+int launch_reset_status(Workspace &ws, cudaStream_t s) {
+    reset_status_kernel<<<1, 1, 0, s>>>(ws.d_status);
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
 int launch_select(const Index &ix, Workspace &ws, int nq, int k, int metric, FilterSpec fs, cudaStream_t s) {
     (void)ix;
     (void)metric;
     if (nq <= 0) return PKV_OK;
     const size_t smem = (size_t)ws.cap * sizeof(uint64_t);
     PKV_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reset_status_kernel<<<1, 1, 0, s>>>(ws.d_status);
     select_kernel<<<nq, 512, smem, s>>>(ws.d_cand, ws.d_cnt, ws.d_thr_key, ws.d_thr_f, ws.d_q_mag_f, ws.d_status,
                                         (uint32_t)ws.cap, k, fs);
     PKV_CUDA(cudaGetLastError());

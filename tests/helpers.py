@@ -31,6 +31,17 @@ def _first_diff(a, b, c, d):
     return f"first difference at {i}: got {a[i]} want {b[i]} (aux got {np.asarray(c)[i]} want {np.asarray(d)[i]}); {len(idx)} differing entries"
 
 
+def _tol(d, metric, rtol, atol):
+    """Allowed |difference| for oracle distance(s) d.  Cosine: the *score* is the cosine similarity
+    1 - d, so 1e-5 relative on the score is rtol * max(|d|, |1 - d|) on the distance (for
+    near-duplicate vectors d ~ 1e-6 is a cancellation of O(1) sums and no summation order can hold
+    1e-5 relative on d itself).  L2 / DOT: relative on the distance."""
+    d = np.abs(d)
+    if metric == orc.COSINE:
+        return rtol * np.maximum(d, np.abs(1.0 - d)) + atol
+    return rtol * d + atol
+
+
 def assert_close_topk(got, want, corpus, queries, metric, rtol=F32_RTOL, atol=1e-7):
     """f32 parity: the GPU sums in a different order than the scalar loop, so distances agree
     to `rtol` and ids may differ only where the oracle's own distances are that close."""
@@ -44,7 +55,7 @@ def assert_close_topk(got, want, corpus, queries, metric, rtol=F32_RTOL, atol=1e
         nan_g, nan_o = np.isnan(dg), np.isnan(do)
         assert np.array_equal(nan_g, nan_o), f"query {q}: NaN placement differs"
         ok = ~nan_o
-        tol = rtol * np.abs(do[ok]) + atol
+        tol = _tol(do[ok], metric, rtol, atol)
         assert np.all(np.abs(dg[ok] - do[ok]) <= tol), (
             f"query {q}: max rel err {np.max(np.abs(dg[ok]-do[ok])/np.maximum(np.abs(do[ok]),1e-30))}")
         assert np.all(ids_g[q, m:] == -1)
@@ -54,20 +65,20 @@ def assert_close_topk(got, want, corpus, queries, metric, rtol=F32_RTOL, atol=1e
         # and rows only one side returned must sit within rtol of the k-th distance
         d_rows = orc.distances(corpus[ids_g[q, :m]], queries[q], metric)
         fin = ~np.isnan(d_rows)
-        assert np.all(np.abs(d_rows[fin] - dg[fin]) <= rtol * np.abs(d_rows[fin]) + atol), f"query {q}: row distance mismatch"
+        assert np.all(np.abs(d_rows[fin] - dg[fin]) <= _tol(d_rows[fin], metric, rtol, atol)), f"query {q}: row distance mismatch"
         kth = do[ok][-1] if ok.any() else 0.0
         only_g = np.setdiff1d(ids_g[q, :m], rows_o[q, :m])
         only_o = np.setdiff1d(rows_o[q, :m], ids_g[q, :m])
         assert len(only_g) == len(only_o)
         for r in np.concatenate([only_g, only_o]):
             d = orc.distances(corpus[r:r + 1], queries[q], metric)[0]
-            assert abs(d - kth) <= 2 * (rtol * abs(kth) + atol), f"query {q}: row {r} swapped across a gap {abs(d-kth)}"
+            assert abs(d - kth) <= 2 * _tol(kth, metric, rtol, atol), f"query {q}: row {r} swapped across a gap {abs(d-kth)}"
         # rows both sides returned may be permuted only within near-ties
         pos_o = {r: i for i, r in enumerate(rows_o[q, :m])}
         for i, r in enumerate(ids_g[q, :m]):
             j = pos_o.get(r)
             if j is not None and j != i:
-                assert abs(do[j] - do[i]) <= 2 * (rtol * abs(do[i]) + atol) or (np.isnan(do[j]) and np.isnan(do[i]))
+                assert abs(do[j] - do[i]) <= 2 * _tol(do[i], metric, rtol, atol) or (np.isnan(do[j]) and np.isnan(do[i]))
 
 
 def int8_space(n, d, seed=orc.CORPUS_SEED, nq=4):

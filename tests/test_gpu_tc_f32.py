@@ -1,0 +1,70 @@
+"""f32 tensor-core path (tf32 filter + exact FFMA re-scoring): scores within 1e-5 relative of the
+oracle, and the same answer as the CUDA-core kernel (same summation order in the re-scoring)."""
+import numpy as np
+import pytest
+
+import panoptikon_b200 as pk
+from oracle import oracle as orc
+from tests.helpers import assert_close_topk
+
+pytestmark = pytest.mark.gpu
+METRICS = [pk.L2, pk.COSINE, pk.DOT]
+
+
+def _index(x):
+    ix = pk.VectorIndex(x.shape[1], pk.F32)
+    ix.append(x)
+    ix.seal()
+    return ix
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("nq", [17, 128, 300])
+def test_tc_f32_matches_oracle_and_simt(metric, nq):
+    x, q = orc.synthetic(60001, 768, 201), orc.synthetic(nq, 768, 202)
+    with _index(x) as ix:
+        got = ix.search(q, 100, metric)
+        assert ix.counters().last_scan_kind == 4, "tf32 kernel did not run"
+        ix.set_option("force_simt", 1)
+        simt = ix.search(q, 100, metric)
+        assert ix.counters().last_scan_kind == 1
+    want = orc.topk(x, q, metric, 100, threads=16)
+    assert_close_topk(got, want, x, q, metric)
+    assert_close_topk(simt, want, x, q, metric)
+    assert np.array_equal(got[0], simt[0]), "tensor-core and CUDA-core paths returned different ids"
+    assert np.array_equal(got[1].view(np.uint32), simt[1].view(np.uint32)), "paths returned different scores"
+
+
+@pytest.mark.parametrize("dim", [8, 100, 512, 1024, 1536])
+def test_tc_f32_dims_unnormalised(dim):
+    # unnormalised rows with a wide norm spread stress the per-row error bound of the filter
+    rng = np.random.default_rng(11)
+    x = orc.synthetic(5003, dim, 211, normalise=False) * rng.uniform(0.01, 30.0, size=(5003, 1)).astype(np.float32)
+    x[17] = 0.0
+    q = orc.synthetic(40, dim, 212, normalise=False)
+    q[3] *= 100.0
+    with _index(x) as ix:
+        for metric in METRICS:
+            got = ix.search(q, 33, metric)
+            assert ix.counters().last_scan_kind == 4
+            assert_close_topk(got, orc.topk(x, q, metric, 33, threads=8), x, q, metric)
+
+
+def test_tc_f32_near_duplicates_and_bitmap():
+    # clusters of almost identical rows: many pairs sit inside the tf32 error band of the threshold
+    rng = np.random.default_rng(12)
+    centers = orc.synthetic(50, 256, 221)
+    x = np.repeat(centers, 400, axis=0) + rng.standard_normal((20000, 256)).astype(np.float32) * 1e-4
+    x = np.ascontiguousarray(x.astype(np.float32))
+    q = np.ascontiguousarray(centers[:24] + rng.standard_normal((24, 256)).astype(np.float32) * 1e-3)
+    words = (len(x) + 63) // 64
+    bm = np.packbits(rng.random(words * 64) < 0.5, bitorder="little").view(np.uint64)
+    with _index(x) as ix:
+        for metric in (pk.COSINE, pk.L2):
+            assert_close_topk(ix.search(q, 200, metric), orc.topk(x, q, metric, 200, threads=8), x, q, metric)
+        got = ix.search(q, 50, pk.COSINE, bitmap=bm)
+        want = orc.topk(x, q, orc.COSINE, 50, bitmap=bm, threads=8)
+        assert np.array_equal(got[2], want[2])
+        assert np.allclose(got[1], want[1], rtol=1e-5, atol=1e-5)
+        ix.set_option("candidate_capacity", 512)
+        assert_close_topk(ix.search(q, 100, pk.L2), orc.topk(x, q, orc.L2, 100, threads=8), x, q, orc.L2)
