@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--force-simt", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="index option name=value (tuning experiments)")
     return ap.parse_args()
 
 
@@ -236,6 +237,9 @@ def main():
     ix.set_row_base(r0)
     if a.force_simt:
         ix.set_option("force_simt", 1)
+    for kv in a.opt:
+        name, value = kv.split("=")
+        ix.set_option(name, int(value))
     scale = None
     if a.dtype == "i8":
         # global symmetric absmax scale over the whole corpus (docs/vector-int8-quant.md:11-49)

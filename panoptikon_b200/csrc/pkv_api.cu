@@ -735,6 +735,8 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "chunk_growth_x100")) ix.opt.chunk_growth_x100 = value;
     else if (!strcmp(name, "time_kernels")) ix.opt.time_kernels = (int)value;
     else if (!strcmp(name, "tc_min_queries")) ix.opt.tc_min_queries = (int)value;
+    else if (!strcmp(name, "tc_prefetch_tiles")) ix.opt.tc_prefetch_tiles = (int)value;
+    else if (!strcmp(name, "tc_cta2")) ix.opt.tc_cta2 = (int)value;
     else if (!strcmp(name, "tc_min_queries_f32")) ix.opt.tc_min_queries_f32 = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;

@@ -171,6 +171,8 @@ struct Options {
     int64_t chunk_growth_x100 = 0;   // 0 = auto
     int time_kernels = 1;
     int tc_min_queries_f32 = 17;     // f32: the FFMA kernel is HBM-bound up to ~16 queries
+    int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA
+    int tc_cta2 = 1;                 // use the 2-CTA (cta_group::2) kernels when the batch is large enough
     int tc_min_queries = 9;          // below this the CUDA-core kernels are HBM-bound anyway
 };
 

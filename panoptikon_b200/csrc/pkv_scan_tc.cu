@@ -37,7 +37,6 @@ constexpr int TMEM_COLS = 2 * TILE_N;  // double-buffered accumulator
 constexpr int COLS_PER_WARP = TILE_N / 2;
 constexpr int HOLD_CAP = 1536;      // staged pre-filter survivors per CTA
 constexpr int FLUSH_EVERY = 4;      // tiles between cooperative flushes
-constexpr int BOUND_LIM = 1 << 30;
 
 struct TcShared {  // control block behind the data stages
     uint64_t full[MAX_STAGES];
@@ -55,44 +54,6 @@ struct TcShared {  // control block behind the data stages
     int hold_dot[HOLD_CAP];
     uint32_t hold_col[HOLD_CAP];
 };
-
-// Pass decision on the integer dot product d for one (row, query):
-//   COSINE  keep iff  d * rinv >= -thr_f          (rinv = 1/sqrt(aMag))
-//   L2      keep iff  aMag + bMag - 2d <= thr_f
-//   DOT     keep iff  -d <= thr_f
-// NaN (zero-norm row) compares false and is kept, as the SIMT kernel does.
-template <int METRIC>
-__device__ __forceinline__ bool exact_filter(int d, int am, int bm, float thr) {
-    if (METRIC == PKV_COSINE) return !((float)d * rsqrtf((float)am) < -thr);
-    if (METRIC == PKV_L2) return !((float)(am + bm - 2 * d) > thr);
-    return !(-(float)d > thr);
-}
-
-// Per-query figure for the integer pre-filter (computed once per kernel):
-//   COSINE: tneg = -thr_f              bound = tneg * sqrt(am)
-//   L2    : c    = bMag - thr_f        bound = (am + c) / 2
-//   DOT   : tneg = -thr_f              bound = tneg
-// +inf threshold ("keep everything") becomes -1e30, -inf ("keep nothing") +1e30.
-template <int METRIC>
-__device__ __forceinline__ float prefilter_query_figure(float thr, int bm) {
-    float t = METRIC == PKV_L2 ? (float)bm - thr : -thr;
-    if (t != t) t = -1e30f;
-    return fminf(fmaxf(t, -1e30f), 1e30f);
-}
-// Integer bound valid for every row of the warp: a pair with d < bound fails exact_filter.
-template <int METRIC>
-__device__ __forceinline__ int prefilter_bound(float tq, float s_min, float s_max, float am_min_f) {
-    float b;
-    if (METRIC == PKV_COSINE)
-        b = tq * (tq >= 0.f ? s_min : s_max);  // loosest norm in the warp
-    else if (METRIC == PKV_L2)
-        b = 0.5f * (am_min_f + tq);
-    else
-        b = tq;
-    b = b - fabsf(b) * 2e-6f - 1.0f;  // rounding slack, floor
-    b = fminf(fmaxf(b, -(float)BOUND_LIM), (float)BOUND_LIM);
-    return __float2int_rd(b);
-}
 
 // Exact filter, exact key, candidate push for one pre-filter survivor.
 template <int METRIC>
@@ -138,7 +99,7 @@ __device__ __forceinline__ void flush_held(const ScanArgs &a, int q0, TcShared *
 template <int METRIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
-                  const ScanArgs a, const int q0, const int kchunks, const int stages) {
+                  const ScanArgs a, const int q0, const int kchunks, const int stages, const int prefetch_tiles) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024-B alignment
@@ -194,6 +155,11 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             uint32_t s = 0, ph = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = (int)(a.row_begin + tile * TILE_M);
+                // pull a tile further ahead into L2: more HBM bytes in flight than the smem ring holds
+                const uint32_t ptile = tile + (uint32_t)prefetch_tiles * gridDim.x;
+                if (prefetch_tiles > 0 && ptile < ntiles)
+                    for (int kc = 0; kc < kchunks; ++kc)
+                        tc::tma_prefetch_2d(&tmap_rows, kc * CHUNK_BYTES, (int)(a.row_begin + ptile * TILE_M));
                 for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->empty[s], ph ^ 1);
                     tc::mbar_expect_tx(&sh->full[s], STAGE_BYTES);
@@ -338,12 +304,15 @@ int launch_metric(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, 
     PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t ntiles = (a.row_end - a.row_begin + TILE_M - 1) / TILE_M;
     const unsigned grid = ntiles < (uint32_t)ix.sm_count ? ntiles : (unsigned)ix.sm_count;
-    kernel<<<grid, TC_THREADS, smem, s>>>(mrows, mq, a, q0, kchunks, stages);
+    kernel<<<grid, TC_THREADS, smem, s>>>(mrows, mq, a, q0, kchunks, stages, ix.opt.tc_prefetch_tiles);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }
 
 }  // namespace
+
+int launch_scan_tc2_tile(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, const CUtensorMap &mq, int q0,
+                         cudaStream_t s);
 
 bool scan_tc_supported(const Index &ix, int nq) {
     if (ix.dtype != PKV_I8 || ix.opt.force_simt) return false;
@@ -364,6 +333,12 @@ int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *laun
     PKV_TRY(make_tmap_bytes(&mq, a.queries, (uint64_t)ix.dim_pad, (uint64_t)a.nq, (uint64_t)ix.dim_pad, TILE_N));
     for (int q0 = 0; q0 < a.nq; q0 += TILE_N) {
         *launches += 1;
+        if (ix.opt.tc_cta2 && a.nq - q0 > TILE_N && (ix.sm_count % 2) == 0) {
+            // 256 queries per corpus pass on a CTA pair (cta_group::2)
+            PKV_TRY(launch_scan_tc2_tile(ix, a, mrows, mq, q0, s));
+            q0 += TILE_N;
+            continue;
+        }
         switch (a.metric) {
             case PKV_COSINE: PKV_TRY(launch_metric<PKV_COSINE>(ix, a, mrows, mq, q0, kchunks, stages, smem, s)); break;
             case PKV_L2: PKV_TRY(launch_metric<PKV_L2>(ix, a, mrows, mq, q0, kchunks, stages, smem, s)); break;

@@ -53,7 +53,7 @@ template <int NQ, int METRIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
                    const ScanArgs a, const PendDev pend, const int q0, const int kchunks, const int stages,
-                   const float eps) {
+                   const float eps, const int prefetch_tiles) {
     constexpr int Q_BYTES = NQ * CHUNK_BYTES;
     constexpr int STAGE = A_BYTES + Q_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -102,6 +102,10 @@ scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
             uint32_t it = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = (int)(a.row_begin + tile * TILE_M);
+                const uint32_t ptile = tile + (uint32_t)prefetch_tiles * gridDim.x;
+                if (prefetch_tiles > 0 && ptile < ntiles)
+                    for (int kc = 0; kc < kchunks; ++kc)
+                        tc::tma_prefetch_2d(&tmap_rows, kc * CHUNK_BYTES, (int)(a.row_begin + ptile * TILE_M));
                 for (int kc = 0; kc < kchunks; ++kc, ++it) {
                     const uint32_t s = it % stages, ph = (it / stages) & 1;
                     tc::mbar_wait(&sh->empty[s], ph ^ 1);
@@ -274,7 +278,8 @@ int launch_one(const Index &ix, const ScanArgs &a, const PendDev &pend, const CU
     PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t ntiles = (a.row_end - a.row_begin + TILE_M - 1) / TILE_M;
     const unsigned grid = ntiles < (uint32_t)ix.sm_count ? ntiles : (unsigned)ix.sm_count;
-    kernel<<<grid, TC_THREADS, smem, s>>>(mrows, mq, a, pend, q0, ix.dim_pad * 4 / CHUNK_BYTES, stages, eps);
+    kernel<<<grid, TC_THREADS, smem, s>>>(mrows, mq, a, pend, q0, ix.dim_pad * 4 / CHUNK_BYTES, stages, eps,
+                                          ix.opt.tc_prefetch_tiles);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }

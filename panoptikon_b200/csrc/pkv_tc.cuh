@@ -118,6 +118,75 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- 2-CTA (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's smem, completion bytes credited to the mbarrier at cluster address `bar`
+__device__ __forceinline__ void tma_load_2d_cta2(void *smem_dst, const CUtensorMap *tmap, uint32_t bar_cluster_addr,
+                                                 int c_inner, int c_row) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_row)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cta2(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cta2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cta2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_i8_cta2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_tf32_cta2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this smem offset in BOTH CTAs of the pair once prior MMAs are done
+__device__ __forceinline__ void mma_commit_cta2(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// L2 prefetch of a future TMA box (no smem, no barrier): keeps more HBM traffic in flight
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tmap, int c_inner, int c_row) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c_inner), "r"(c_row)
+                 : "memory");
+}
+
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ----
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO),
 // LBO is unused for swizzled K-major layouts (1), descriptor version 1 (sm_100).
@@ -134,4 +203,46 @@ __host__ __device__ constexpr uint32_t make_idesc(int c_format, int ab_format, i
 }
 
 }  // namespace tc
+
+// ---- int8 epilogue arithmetic shared by the 1-CTA and 2-CTA kernels ----
+constexpr int BOUND_LIM = 1 << 30;
+
+// Pass decision on the integer dot product d for one (row, query):
+//   COSINE  keep iff  d * rinv >= -thr_f          (rinv = 1/sqrt(aMag))
+//   L2      keep iff  aMag + bMag - 2d <= thr_f
+//   DOT     keep iff  -d <= thr_f
+// NaN (zero-norm row) compares false and is kept, as the SIMT kernel does.
+template <int METRIC>
+__device__ __forceinline__ bool exact_filter(int d, int am, int bm, float thr) {
+    if (METRIC == PKV_COSINE) return !((float)d * rsqrtf((float)am) < -thr);
+    if (METRIC == PKV_L2) return !((float)(am + bm - 2 * d) > thr);
+    return !(-(float)d > thr);
+}
+
+// Per-query figure for the integer pre-filter (computed once per kernel):
+//   COSINE: tneg = -thr_f              bound = tneg * sqrt(am)
+//   L2    : c    = bMag - thr_f        bound = (am + c) / 2
+//   DOT   : tneg = -thr_f              bound = tneg
+// +inf threshold ("keep everything") becomes -1e30, -inf ("keep nothing") +1e30.
+template <int METRIC>
+__device__ __forceinline__ float prefilter_query_figure(float thr, int bm) {
+    float t = METRIC == PKV_L2 ? (float)bm - thr : -thr;
+    if (t != t) t = -1e30f;
+    return fminf(fmaxf(t, -1e30f), 1e30f);
+}
+// Integer bound valid for every row of the warp: a pair with d < bound fails exact_filter.
+template <int METRIC>
+__device__ __forceinline__ int prefilter_bound(float tq, float s_min, float s_max, float am_min_f) {
+    float b;
+    if (METRIC == PKV_COSINE)
+        b = tq * (tq >= 0.f ? s_min : s_max);  // loosest norm in the warp
+    else if (METRIC == PKV_L2)
+        b = 0.5f * (am_min_f + tq);
+    else
+        b = tq;
+    b = b - fabsf(b) * 2e-6f - 1.0f;  // rounding slack, floor
+    b = fminf(fmaxf(b, -(float)BOUND_LIM), (float)BOUND_LIM);
+    return __float2int_rd(b);
+}
+
 }  // namespace pkv

@@ -21,7 +21,7 @@ def _index(xc, scale=None):
 
 
 @pytest.mark.parametrize("metric", METRICS)
-@pytest.mark.parametrize("nq", [9, 128, 130])
+@pytest.mark.parametrize("nq", [9, 128, 130, 300, 513])
 def test_tc_int8_bit_exact(metric, nq):
     x, q, scale, xc, qc = int8_space(70001, 768, 101, nq)
     with _index(xc, scale) as ix:
@@ -78,3 +78,16 @@ def test_tc_adversarial_order():
         got = ix.search(qc, 50, pk.COSINE)
         assert ix.counters().fallback_queries > 0
     assert_exact(got, orc.topk(xc, qc, orc.COSINE, 50, threads=8))
+
+
+def test_tc_cta_pair_matches_single_cta():
+    # 256 queries per pass on a CTA pair (cta_group::2) vs two 128-query passes on single CTAs
+    x, q, scale, xc, qc = int8_space(90011, 512, 121, 256)
+    with _index(xc, scale) as ix:
+        for metric in METRICS:
+            pair = ix.search(qc, 64, metric)
+            ix.set_option("tc_cta2", 0)
+            single = ix.search(qc, 64, metric)
+            ix.set_option("tc_cta2", 1)
+            assert_exact(pair, single)
+            assert_exact(pair, orc.topk(xc, qc, metric, 64, threads=16))
