@@ -2,6 +2,7 @@
 // scan/select search driver, codec entry points.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -62,6 +63,8 @@ Workspace::~Workspace() {
     cudaFree(d_status);
     cudaFree(d_pend_rows);
     cudaFree(d_pend_cnt);
+    cudaFree(d_q16);
+    cudaFree(d_q_scale);
     if (h_status) cudaFreeHost(h_status);
     cudaFree(d_out_ids);
     cudaFree(d_out_dist);
@@ -127,9 +130,11 @@ static int make_workspace(Index &ix, int nq, int k, size_t out_rows, Workspace *
         A((void **)&ws->d_thr_key, sizeof(uint64_t) * nq_cap);
         A((void **)&ws->d_thr_f, sizeof(float) * nq_cap);
         A((void **)&ws->d_status, sizeof(SearchStatus));
-        if (ix.dtype == PKV_F32) {
+        if (ix.dtype != PKV_I8) {
             A((void **)&ws->d_pend_rows, sizeof(uint32_t) * (size_t)nq_cap * cap);
             A((void **)&ws->d_pend_cnt, sizeof(uint32_t) * nq_cap);
+            A((void **)&ws->d_q16, sizeof(__half) * (size_t)nq_cap * ix.dim_pad_h);
+            A((void **)&ws->d_q_scale, sizeof(float) * nq_cap);
         }
         A((void **)&ws->d_out_ids, sizeof(int64_t) * out_rows);
         A((void **)&ws->d_out_dist, sizeof(float) * out_rows);
@@ -176,10 +181,13 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e) {
     if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[0], r.s));
     int n = 0;
     PKV_TRY(launch_reset_status(r.ws, r.s));
-    if (r.use_tc_f32)
-        PKV_TRY(launch_scan_tc_f32(r.ix, r.args, r.ws.d_pend_rows, r.ws.d_pend_cnt, (uint32_t)r.ws.cap, r.ws.d_status,
-                                   r.s, &n));
-    else if (r.use_tc)
+    // While some query has no threshold yet every pair is a candidate: that is dense work with one
+    // push per pair, which the CUDA-core kernel does far more cheaply than the tensor-core
+    // kernels' survivor path (built for rare survivors).
+    const bool bootstrap = r.min_filled < (uint32_t)r.k && (e - b) <= r.safe_rows && r.ix.opt.simt_bootstrap;
+    if (r.use_tc_f32 && !bootstrap)
+        PKV_TRY(launch_scan_tc_f32(r.ix, r.args, r.ws, r.s, &n));
+    else if (r.use_tc && !bootstrap)
         PKV_TRY(launch_scan_tc(r.ix, r.args, r.s, &n));
     else
         PKV_TRY(launch_scan_simt(r.ix, r.args, r.s, &n));
@@ -197,6 +205,17 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e) {
     }
     const SearchStatus st = *r.ws.h_status;
     r.min_filled = st.min_filled;
+    static const bool trace = getenv("PKV_TRACE") != nullptr;
+    if (trace && timed) {
+        float ms = 0.f, ms2 = 0.f;
+        cudaEventElapsedTime(&ms, r.ws.ev[0], r.ws.ev[1]);
+        cudaEventRecord(r.ws.ev[0], r.s);
+        cudaEventSynchronize(r.ws.ev[0]);
+        cudaEventElapsedTime(&ms2, r.ws.ev[1], r.ws.ev[0]);
+        fprintf(stderr, "[pkv] rows [%lld,%lld) nq %d: scan %.3f ms (%.0f GB/s), select+sync %.3f ms, max_raw_cnt %u, overflow %u\n",
+                (long long)b, (long long)e, r.nq, ms, (double)(e - b) * r.ix.pitch / (ms * 1e6), ms2, st.max_raw_cnt,
+                st.any_overflow);
+    }
     if (st.any_overflow) {
         // Some query pushed more candidates than its buffer holds.  The select kept the best k
         // of what fitted (all real rows, so the thresholds only got tighter); re-scan the range
@@ -226,7 +245,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     r.launches = 2;
     r.use_tc = scan_tc_supported(ix, nq);
     r.use_tc_f32 = scan_tc_f32_supported(ix, nq);
-    if (r.use_tc_f32) r.fs = filter_spec_tc_f32(p.metric);
+    if (r.use_tc_f32) r.fs = filter_spec_tc_f32(ix, p.metric);
     ScanArgs &a = r.args;
     a.data = ix.d_data;
     a.pitch_bytes = ix.pitch;
@@ -277,7 +296,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     ix.n_scan_launches += r.scan_launches;
     ix.n_fallback += r.depth_overflows;
     ix.last_scan_ms += r.scan_ms;
-    ix.last_scan_kind = r.use_tc_f32 ? 4 : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
+    ix.last_scan_kind = r.use_tc_f32 ? scan_tc_f32_kind(ix) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
     return PKV_OK;
 }
 
@@ -393,7 +412,10 @@ static int grow(Index &ix, int64_t need_rows, bool exact = false) {
     int32_t *nmi = nullptr;
     float *nmf = nullptr;
     int64_t *nids = nullptr;
+    __half *nsh = nullptr;
     cudaError_t e = cudaMalloc((void **)&nd, (size_t)cap * ix.pitch);
+    if (e == cudaSuccess && ix.dtype == PKV_F32 && ix.opt.use_shadow)
+        e = cudaMalloc((void **)&nsh, (size_t)cap * ix.dim_pad_h * sizeof(__half));
     if (e == cudaSuccess && ix.dtype == PKV_I8) e = cudaMalloc((void **)&nmi, sizeof(int32_t) * cap);
     if (e == cudaSuccess && ix.dtype != PKV_I8) e = cudaMalloc((void **)&nmf, sizeof(float) * cap);
     if (e == cudaSuccess && ix.d_ids) e = cudaMalloc((void **)&nids, sizeof(int64_t) * cap);
@@ -402,6 +424,7 @@ static int grow(Index &ix, int64_t need_rows, bool exact = false) {
         cudaFree(nmi);
         cudaFree(nmf);
         cudaFree(nids);
+        cudaFree(nsh);
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? PKV_ERR_OOM : PKV_ERR_CUDA,
                     "cannot reserve %lld rows (%lld bytes): %s", (long long)cap, (long long)(cap * ix.pitch),
@@ -412,11 +435,16 @@ static int grow(Index &ix, int64_t need_rows, bool exact = false) {
         if (nmi) PKV_CUDA(cudaMemcpy(nmi, ix.d_mag_i, sizeof(int32_t) * ix.rows, cudaMemcpyDeviceToDevice));
         if (nmf) PKV_CUDA(cudaMemcpy(nmf, ix.d_mag_f, sizeof(float) * ix.rows, cudaMemcpyDeviceToDevice));
         if (nids) PKV_CUDA(cudaMemcpy(nids, ix.d_ids, sizeof(int64_t) * ix.rows, cudaMemcpyDeviceToDevice));
+        if (nsh && ix.d_shadow)
+            PKV_CUDA(cudaMemcpy(nsh, ix.d_shadow, (size_t)ix.sealed_rows * ix.dim_pad_h * sizeof(__half),
+                                cudaMemcpyDeviceToDevice));
     }
     cudaFree(ix.d_data);
     cudaFree(ix.d_mag_i);
     cudaFree(ix.d_mag_f);
     cudaFree(ix.d_ids);
+    cudaFree(ix.d_shadow);
+    ix.d_shadow = nsh;
     ix.d_data = nd;
     ix.d_mag_i = nmi;
     ix.d_mag_f = nmf;
@@ -583,6 +611,7 @@ int pkv_index_create(int device, int dim, int dtype, pkv_index **out) {
     ix->elem = elem_size(dtype);
     ix->dim_pad = pad_dim(dim, dtype);
     ix->pitch = (int64_t)ix->dim_pad * ix->elem;
+    ix->dim_pad_h = (dim + 63) / 64 * 64;
     ix->sm_count = prop.multiProcessorCount;
     *out = reinterpret_cast<pkv_index *>(ix);
     return PKV_OK;
@@ -597,6 +626,7 @@ int pkv_index_destroy(pkv_index *h) {
     cudaFree(ix->d_ids);
     cudaFree(ix->d_mag_i);
     cudaFree(ix->d_mag_f);
+    cudaFree(ix->d_shadow);
     delete ix;
     return PKV_OK;
 }
@@ -649,6 +679,30 @@ int pkv_index_seal(pkv_index *h) {
     std::unique_lock<std::shared_mutex> lock(ix.mu);
     if (ix.sealed_rows < ix.rows) {
         PKV_TRY(launch_row_mags(ix, ix.sealed_rows, ix.rows, nullptr));
+        if (ix.dtype == PKV_F32 && ix.d_shadow) {
+            // fp16 image of the new rows, scaled by a power of two so that the largest component of
+            // the whole index lands in [8192, 16384): exact scaling, no overflow, tiny values keep
+            // full relative precision down to 2^-14/16384 of the largest one
+            float *d_am = nullptr, am = 0.f;
+            PKV_CUDA(cudaMalloc((void **)&d_am, sizeof(float)));
+            int st = launch_absmax((const float *)(ix.d_data + (size_t)ix.sealed_rows * ix.pitch),
+                                   (ix.rows - ix.sealed_rows) * (int64_t)ix.dim_pad, d_am, nullptr);
+            cudaError_t ce = cudaMemcpy(&am, d_am, sizeof(float), cudaMemcpyDeviceToHost);
+            cudaFree(d_am);
+            PKV_TRY(st);
+            PKV_CUDA(ce);
+            int64_t from = ix.sealed_rows;
+            const bool finite = am <= 3.0e38f;
+            if (finite && am > ix.shadow_absmax) ix.shadow_absmax = am;
+            if (ix.shadow_scale == 0.f || ix.shadow_absmax * ix.shadow_scale >= 32768.f) {
+                float sc = 1.0f;
+                if (ix.shadow_absmax > 0.f) sc = ldexpf(1.0f, 13 - ilogbf(ix.shadow_absmax));
+                if (!(sc > 0.f) || !(sc <= 3.0e38f)) sc = 1.0f;
+                ix.shadow_scale = sc;
+                from = 0;  // (re)build the whole image with the new scale
+            }
+            PKV_TRY(build_shadow(ix, from, ix.rows, nullptr));
+        }
         PKV_CUDA(cudaDeviceSynchronize());
         ix.sealed_rows = ix.rows;
     }
@@ -668,7 +722,7 @@ int pkv_index_get_info(const pkv_index *h, pkv_index_info *info) {
     info->scale = ix.scale;
     info->rows = ix.rows;
     info->capacity_rows = ix.cap_rows;
-    info->device_bytes = ix.cap_rows * (ix.pitch + 4 + (ix.d_ids ? 8 : 0));
+    info->device_bytes = ix.cap_rows * (ix.pitch + 4 + (ix.d_ids ? 8 : 0) + (ix.d_shadow ? ix.dim_pad_h * 2 : 0));
     info->row_base = ix.row_base;
     return PKV_OK;
 }
@@ -737,6 +791,8 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "tc_min_queries")) ix.opt.tc_min_queries = (int)value;
     else if (!strcmp(name, "tc_prefetch_tiles")) ix.opt.tc_prefetch_tiles = (int)value;
     else if (!strcmp(name, "tc_cta2")) ix.opt.tc_cta2 = (int)value;
+    else if (!strcmp(name, "use_shadow")) ix.opt.use_shadow = (int)value;
+    else if (!strcmp(name, "simt_bootstrap")) ix.opt.simt_bootstrap = (int)value;
     else if (!strcmp(name, "tc_min_queries_f32")) ix.opt.tc_min_queries_f32 = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;

@@ -152,6 +152,8 @@ struct Workspace {
     float *d_thr_f = nullptr;
     uint32_t *d_pend_rows = nullptr;  // tf32 path: rows awaiting exact re-scoring, [nq_cap][cap]
     uint32_t *d_pend_cnt = nullptr;
+    __half *d_q16 = nullptr;          // fp16-image path: scaled half queries [nq_cap][dim_pad_h]
+    float *d_q_scale = nullptr;       // accumulator -> dot factor per query
     SearchStatus *d_status = nullptr;
     SearchStatus *h_status = nullptr;  // pinned
     int64_t *d_out_ids = nullptr;
@@ -171,6 +173,8 @@ struct Options {
     int64_t chunk_growth_x100 = 0;   // 0 = auto
     int time_kernels = 1;
     int tc_min_queries_f32 = 17;     // f32: the FFMA kernel is HBM-bound up to ~16 queries
+    int simt_bootstrap = 1;          // threshold-less first chunk runs on the CUDA-core kernel
+    int use_shadow = 1;              // f32 index: keep a scaled fp16 image for the tensor-core filter
     int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA
     int tc_cta2 = 1;                 // use the 2-CTA (cta_group::2) kernels when the batch is large enough
     int tc_min_queries = 9;          // below this the CUDA-core kernels are HBM-bound anyway
@@ -189,6 +193,10 @@ struct Index {
     int64_t ids_rows = 0;       // rows of d_ids that are initialised
     int32_t *d_mag_i = nullptr; // int8 row sums of squares
     float *d_mag_f = nullptr;   // f32/f16 row sums of squares (tensor-core paths)
+    __half *d_shadow = nullptr; // f32 index: power-of-two-scaled fp16 image of the rows (filter operand)
+    int dim_pad_h = 0;          // components per fp16 image row (multiple of 64)
+    float shadow_scale = 0.f;   // 0 = image not built yet
+    float shadow_absmax = 0.f;
     bool has_scale = false;
     float scale = 1.0f;
     int sm_count = 148;
@@ -210,9 +218,11 @@ bool scan_tc_supported(const Index &ix, int nq);
 int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches);
 // pkv_scan_tc_f32.cu (tf32 filter + exact re-scoring)
 bool scan_tc_f32_supported(const Index &ix, int nq);
-FilterSpec filter_spec_tc_f32(int metric);
-int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, uint32_t *d_pend_rows, uint32_t *d_pend_cnt,
-                       uint32_t pend_cap, SearchStatus *d_status, cudaStream_t s, int *launches);
+FilterSpec filter_spec_tc_f32(const Index &ix, int metric);
+int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches);
+int scan_tc_f32_kind(const Index &ix);
+int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);
+
 // pkv_topk.cu
 int launch_reset_status(Workspace &ws, cudaStream_t s);
 int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);

@@ -35,8 +35,8 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 2 * TILE_N;  // double-buffered accumulator
 constexpr int COLS_PER_WARP = TILE_N / 2;
-constexpr int HOLD_CAP = 1536;      // staged pre-filter survivors per CTA
-constexpr int FLUSH_EVERY = 4;      // tiles between cooperative flushes
+constexpr int HOLD_CAP = 160;       // staged pre-filter survivors per epilogue warp
+constexpr int HOLD_FLUSH = 96;      // flush (lane-parallel) once this many are parked
 
 struct TcShared {  // control block behind the data stages
     uint64_t full[MAX_STAGES];
@@ -45,14 +45,15 @@ struct TcShared {  // control block behind the data stages
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
-    uint32_t hold_cnt;
+    uint32_t pad;
+    uint32_t hold_cnt[EPI_WARPS];
     alignas(16) float thr[TILE_N];  // per query: filter threshold thr_f (metric specific)
     float tq[TILE_N];        // per query: finite, clamped figure the integer bound is derived from
     int q_mag[TILE_N];       // per query: integer squared norm
     alignas(16) int bound[EPI_WARPS][COLS_PER_WARP];  // per epilogue warp: integer pre-filter bound, current tile
-    uint32_t hold_row[HOLD_CAP];          // pre-filter survivors waiting for the lane-parallel flush
-    int hold_dot[HOLD_CAP];
-    uint32_t hold_col[HOLD_CAP];
+    uint32_t hold_row[EPI_WARPS][HOLD_CAP];  // pre-filter survivors waiting for the lane-parallel flush
+    int hold_dot[EPI_WARPS][HOLD_CAP];
+    uint32_t hold_col[EPI_WARPS][HOLD_CAP];
 };
 
 // Exact filter, exact key, candidate push for one pre-filter survivor.
@@ -69,31 +70,32 @@ __device__ __noinline__ void consider(const ScanArgs &a, int q0, int col, int d,
     topk_push(a.topk, q, row, i8_key(METRIC, d, am, bm, a.dim, rowp, qp));
 }
 
-// A lane found a survivor: park it in shared memory (cheap) so that the expensive part runs
-// later with 32 survivors per warp in flight instead of one.
+// A lane found a pre-filter survivor: park it in its warp's shared-memory list (cheap) so that the
+// expensive part runs later with 32 survivors per warp in flight instead of one.
 template <int METRIC>
-__device__ __noinline__ void hold(const ScanArgs &a, int q0, int col, int d, uint32_t row, TcShared *sh) {
-    const uint32_t slot = atomicAdd(&sh->hold_cnt, 1u);
+__device__ __noinline__ void hold(const ScanArgs &a, int q0, int col, int d, uint32_t row, TcShared *sh, int ew) {
+    const uint32_t slot = atomicAdd(&sh->hold_cnt[ew], 1u);
     if (slot < HOLD_CAP) {
-        sh->hold_row[slot] = row;
-        sh->hold_dot[slot] = d;
-        sh->hold_col[slot] = (uint32_t)col;
+        sh->hold_row[ew][slot] = row;
+        sh->hold_dot[ew][slot] = d;
+        sh->hold_col[ew][slot] = (uint32_t)col;
     } else {
-        consider<METRIC>(a, q0, col, d, row, sh);  // buffer full (unthresholded first chunk): do it now
+        consider<METRIC>(a, q0, col, d, row, sh);  // list full (unthresholded first chunk): do it now
     }
 }
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
-
+// Warp-private flush: no CTA-wide barrier, only __syncwarp.
 template <int METRIC>
-__device__ __forceinline__ void flush_held(const ScanArgs &a, int q0, TcShared *sh, int epi_tid) {
-    epi_barrier();
-    const uint32_t n = sh->hold_cnt < HOLD_CAP ? sh->hold_cnt : HOLD_CAP;
-    for (uint32_t e = epi_tid; e < n; e += EPI_THREADS)
-        consider<METRIC>(a, q0, (int)sh->hold_col[e], sh->hold_dot[e], sh->hold_row[e], sh);
-    epi_barrier();
-    if (epi_tid == 0) sh->hold_cnt = 0;
-    epi_barrier();
+__device__ __forceinline__ void flush_held(const ScanArgs &a, int q0, TcShared *sh, int ew, int lane, uint32_t min_cnt) {
+    __syncwarp();
+    const uint32_t cnt = sh->hold_cnt[ew];
+    if (cnt < min_cnt) return;
+    const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
+    for (uint32_t e = lane; e < n; e += 32)
+        consider<METRIC>(a, q0, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+    __syncwarp();
+    if (lane == 0) sh->hold_cnt[ew] = 0;
+    __syncwarp();
 }
 
 template <int METRIC>
@@ -121,7 +123,7 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             tc::mbar_init(&sh->tmem_full[b], 1);
             tc::mbar_init(&sh->tmem_empty[b], EPI_WARPS);
         }
-        sh->hold_cnt = 0;
+        for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_rows);
         tc::prefetch_tmap(&tmap_q);
@@ -199,7 +201,6 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
     } else {
         // ===================== epilogue =====================
         const int ew = warp - 2;           // 0..7
-        const int epi_tid = threadIdx.x - 64;
         const int quarter = warp & 3;      // TMEM lane quarter this warp may access
         const int half = ew >> 2;          // which 64 columns
         const int col0 = half * COLS_PER_WARP;
@@ -242,16 +243,16 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int d = (int)v[j];
-                        if (d >= sh->bound[ew][c * 32 + j]) hold<METRIC>(a, q0, col0 + c * 32 + j, d, cur_row, sh);
+                        if (d >= sh->bound[ew][c * 32 + j]) hold<METRIC>(a, q0, col0 + c * 32 + j, d, cur_row, sh, ew);
                     }
                 }
             }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
-            if ((t % FLUSH_EVERY) == FLUSH_EVERY - 1) flush_held<METRIC>(a, q0, sh, epi_tid);
+            flush_held<METRIC>(a, q0, sh, ew, lane, HOLD_FLUSH);
         }
-        flush_held<METRIC>(a, q0, sh, epi_tid);
+        flush_held<METRIC>(a, q0, sh, ew, lane, 1);
     }
 
     tc::fence_before_sync();

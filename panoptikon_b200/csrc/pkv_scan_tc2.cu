@@ -31,8 +31,8 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 2 * QN;  // double-buffered 128 x 256 accumulator: the whole TMEM
 constexpr int COLS_PER_WARP = QN / 2;
-constexpr int HOLD_CAP = 1024;
-constexpr int FLUSH_EVERY = 4;
+constexpr int HOLD_CAP = 160;    // staged pre-filter survivors per epilogue warp
+constexpr int HOLD_FLUSH = 96;   // flush (lane-parallel) once this many are parked
 
 struct Tc2Shared {
     uint64_t full[MAX_STAGES];
@@ -41,14 +41,15 @@ struct Tc2Shared {
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
-    uint32_t hold_cnt;
+    uint32_t pad;
+    uint32_t hold_cnt[EPI_WARPS];
     alignas(16) float thr[QN];
     alignas(16) float tq[QN];
     alignas(16) int q_mag[QN];
     alignas(16) int bound[EPI_WARPS][COLS_PER_WARP];
-    uint32_t hold_row[HOLD_CAP];
-    int hold_dot[HOLD_CAP];
-    uint32_t hold_col[HOLD_CAP];
+    uint32_t hold_row[EPI_WARPS][HOLD_CAP];
+    int hold_dot[EPI_WARPS][HOLD_CAP];
+    uint32_t hold_col[EPI_WARPS][HOLD_CAP];
 };
 
 template <int METRIC>
@@ -64,29 +65,32 @@ __device__ __noinline__ void consider2(const ScanArgs &a, int q0, int col, int d
     topk_push(a.topk, q, row, i8_key(METRIC, d, am, bm, a.dim, rowp, qp));
 }
 
+// A lane found a pre-filter survivor: park it in its warp's shared-memory list (cheap) so that the
+// expensive part runs later with 32 survivors per warp in flight instead of one.
 template <int METRIC>
-__device__ __noinline__ void hold2(const ScanArgs &a, int q0, int col, int d, uint32_t row, Tc2Shared *sh) {
-    const uint32_t slot = atomicAdd(&sh->hold_cnt, 1u);
+__device__ __noinline__ void hold2(const ScanArgs &a, int q0, int col, int d, uint32_t row, Tc2Shared *sh, int ew) {
+    const uint32_t slot = atomicAdd(&sh->hold_cnt[ew], 1u);
     if (slot < HOLD_CAP) {
-        sh->hold_row[slot] = row;
-        sh->hold_dot[slot] = d;
-        sh->hold_col[slot] = (uint32_t)col;
+        sh->hold_row[ew][slot] = row;
+        sh->hold_dot[ew][slot] = d;
+        sh->hold_col[ew][slot] = (uint32_t)col;
     } else {
-        consider2<METRIC>(a, q0, col, d, row, sh);
+        consider2<METRIC>(a, q0, col, d, row, sh);  // list full (unthresholded first chunk): do it now
     }
 }
 
-__device__ __forceinline__ void epi_barrier2() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
-
+// Warp-private flush: no CTA-wide barrier, only __syncwarp.
 template <int METRIC>
-__device__ __forceinline__ void flush_held2(const ScanArgs &a, int q0, Tc2Shared *sh, int epi_tid) {
-    epi_barrier2();
-    const uint32_t n = sh->hold_cnt < HOLD_CAP ? sh->hold_cnt : HOLD_CAP;
-    for (uint32_t e = epi_tid; e < n; e += EPI_THREADS)
-        consider2<METRIC>(a, q0, (int)sh->hold_col[e], sh->hold_dot[e], sh->hold_row[e], sh);
-    epi_barrier2();
-    if (epi_tid == 0) sh->hold_cnt = 0;
-    epi_barrier2();
+__device__ __forceinline__ void flush_held2(const ScanArgs &a, int q0, Tc2Shared *sh, int ew, int lane, uint32_t min_cnt) {
+    __syncwarp();
+    const uint32_t cnt = sh->hold_cnt[ew];
+    if (cnt < min_cnt) return;
+    const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
+    for (uint32_t e = lane; e < n; e += 32)
+        consider2<METRIC>(a, q0, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+    __syncwarp();
+    if (lane == 0) sh->hold_cnt[ew] = 0;
+    __syncwarp();
 }
 
 template <int METRIC>
@@ -116,7 +120,7 @@ scan_i8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
             tc::mbar_init(&sh->tmem_full[b], 1);
             tc::mbar_init(&sh->tmem_empty[b], 2 * EPI_WARPS);
         }
-        sh->hold_cnt = 0;
+        for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_rows);
         tc::prefetch_tmap(&tmap_q);
@@ -197,7 +201,6 @@ scan_i8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     } else {
         // ===================== epilogue (both CTAs, own 128 rows x 256 queries) =====================
         const int ew = warp - 2;
-        const int epi_tid = threadIdx.x - 64;
         const int quarter = warp & 3;
         const int col0 = (ew >> 2) * COLS_PER_WARP;
         const uint32_t row_off = rank * ROWS_PER_CTA + quarter * 32 + lane;
@@ -239,16 +242,16 @@ scan_i8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int d = (int)v[j];
-                        if (d >= sh->bound[ew][c * 32 + j]) hold2<METRIC>(a, q0, col0 + c * 32 + j, d, cur_row, sh);
+                        if (d >= sh->bound[ew][c * 32 + j]) hold2<METRIC>(a, q0, col0 + c * 32 + j, d, cur_row, sh, ew);
                     }
                 }
             }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(buf ? empty1 : empty0);
-            if ((t % FLUSH_EVERY) == FLUSH_EVERY - 1) flush_held2<METRIC>(a, q0, sh, epi_tid);
+            flush_held2<METRIC>(a, q0, sh, ew, lane, HOLD_FLUSH);
         }
-        flush_held2<METRIC>(a, q0, sh, epi_tid);
+        flush_held2<METRIC>(a, q0, sh, ew, lane, 1);
     }
 
     tc::fence_before_sync();
@@ -282,9 +285,6 @@ int launch2(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, const 
 }
 
 }  // namespace
-
-int make_tmap_bytes(CUtensorMap *m, const void *base, uint64_t inner_bytes, uint64_t rows, uint64_t pitch_bytes,
-                    uint32_t box_rows);
 
 // One pass of the 2-CTA kernel over [row_begin,row_end) for queries [q0, q0+256).
 int launch_scan_tc2_tile(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, const CUtensorMap &mq, int q0,

@@ -1,23 +1,30 @@
-// pkv_scan_tc_f32.cu — tensor-core scan for f32 rows: tcgen05.mma kind::tf32 as a conservative
-// FILTER, exact f32 re-scoring of the survivors.
+// pkv_scan_tc_f32.cu — tensor-core scan for floating-point rows (f32 and f16 indexes): a reduced-
+// precision tcgen05 contraction as a conservative FILTER, exact f32 re-scoring of the survivors.
 //
 // Why a filter: at 256 queries per pass the f32 scan needs 2*256 flop per 4 corpus bytes, ~20x what
-// the FFMA pipe delivers at HBM speed, so the contraction has to run on tensor cores; but TF32
-// keeps 10 mantissa bits and cannot meet the 1e-5 relative tolerance on the score.  So the TF32
-// dot product only decides which (row, query) pairs MAY belong to the top-k — with a rigorous
-// error bound |dot~ - dot| <= eps * |a| * |b| folded into the threshold — and those pairs (a few
-// thousand per query per pass) are re-scored by rescore_f32_kernel with the same FFMA summation
-// order as the CUDA-core scan, so scores and ids do not depend on which path ran.
+// the FFMA pipe delivers at HBM speed, so the contraction has to run on tensor cores; but no
+// tensor-core input format meets the 1e-5 relative tolerance on the score.  So the tensor-core dot
+// product only decides which (row, query) pairs MAY belong to the top-k — with a rigorous error
+// bound |dot~ - dot| <= eps * |a| * |q| folded into the threshold — and those pairs (a few thousand
+// per query per pass) are re-scored by rescore_kernel from the exact stored rows with the same
+// FFMA summation order as the CUDA-core scan, so scores and ids do not depend on which path ran.
+//
+// Two operand formats (template KIND):
+//   KIND_TF32  rows read as stored (f32), kind::tf32, eps = 2.2e-3 (>= 2^-9: 10-bit mantissas)
+//   KIND_F16   rows read from an fp16 image: the index's power-of-two-scaled fp16 SHADOW of its
+//              f32 rows (half the HBM bytes and twice the tensor rate of tf32, eps = 1.25e-3), or
+//              the rows themselves for an f16 index (eps = 2e-4: only accumulation error)
 //
 // Replaces vec_distance_cosine / vec_distance_L2 over `embeddings.embedding` blobs
 // (pql/builder/filters/image_embeddings.rs:321-337, text_embeddings.rs:386-393).
 //
 // Pipeline per CTA (one per SM): TMA producer warp streams, per 128-byte K-chunk, 128 corpus
-// rows AND the matching chunk of NQ queries (queries come from L2: a 256-query f32 tile is
-// 786 KB and cannot stay resident in shared memory); MMA warp issues M=128 x N=NQ x K=8 UMMAs
-// into a double-buffered TMEM accumulator; four epilogue warps threshold it.
+// rows AND the matching chunk of NQ queries (queries come from L2: a 256-query tile does not fit
+// in shared memory next to the stages); MMA warp issues M=128 x N=NQ UMMAs into a double-buffered
+// TMEM accumulator; four epilogue warps threshold it.
 //
-// Algorithmic bytes per row per pass: dim_pad*4 (+4 row norm); flops: 2*NQ*dim_pad per row.
+// Algorithmic bytes per row per pass: the bytes of the image that is scanned (4*D for tf32, 2*D
+// for the fp16 image) + 4 (row norm); flops: 2*NQ*D per row.
 #include "pkv_tc.cuh"
 
 namespace pkv {
@@ -25,22 +32,23 @@ namespace pkv {
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int CHUNK_BYTES = 128;  // 32 f32 components
+constexpr int CHUNK_BYTES = 128;  // 32 f32 or 64 f16 components
 constexpr int A_BYTES = TILE_M * CHUNK_BYTES;
 constexpr int MAX_STAGES = 8;
 constexpr int TC_THREADS = 192;
+constexpr int KIND_TF32 = 0, KIND_F16 = 1;
 
 template <int NQ>
-struct F32Shared {
+struct FShared {
     uint64_t full[MAX_STAGES];
     uint64_t empty[MAX_STAGES];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    alignas(16) float thr[NQ];   // filter threshold per query (see FilterSpec)
-    alignas(16) float qm[NQ];    // |q|^2
-    alignas(16) float qs[NQ];    // eps * |q|  (error-bound scale)
+    // per query: x = threshold in accumulator units (cosine), y = -2*c (c: accumulator -> true dot),
+    //            z = |q|^2 - thr_f (L2) or -thr_f (DOT), w = eps*|q|
+    alignas(16) float4 qv[NQ];
 };
 
 struct PendDev {
@@ -49,21 +57,29 @@ struct PendDev {
     uint32_t cap;
 };
 
-template <int NQ, int METRIC>
+struct FloatScan {
+    const float *q_scale;  // [nq] accumulator -> true dot factor c_q; NULL = 1 (tf32)
+    float eps;             // |dot~ - dot| <= eps |a||q|
+    float tiny_mag;        // rows with |a|^2 below this always go to re-scoring (fp16 image underflow)
+    int prefetch_tiles;
+};
+
+template <int KIND, int NQ, int METRIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
-                   const ScanArgs a, const PendDev pend, const int q0, const int kchunks, const int stages,
-                   const float eps, const int prefetch_tiles) {
+scan_float_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
+                     const ScanArgs a, const PendDev pend, const FloatScan fsn, const int q0, const int kchunks,
+                     const int stages) {
     constexpr int Q_BYTES = NQ * CHUNK_BYTES;
     constexpr int STAGE = A_BYTES + Q_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    F32Shared<NQ> *sh = reinterpret_cast<F32Shared<NQ> *>(smem + (size_t)stages * STAGE);
+    FShared<NQ> *sh = reinterpret_cast<FShared<NQ> *>(smem + (size_t)stages * STAGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nrows = a.row_end - a.row_begin;
     const uint32_t ntiles = (nrows + TILE_M - 1) / TILE_M;
+    const float INF = __int_as_float(0x7f800000);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -85,11 +101,19 @@ scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     if (warp >= 2) {
         for (int col = threadIdx.x - 64; col < NQ; col += 128) {
             const int q = q0 + col;
-            const bool ok = q < a.nq;
-            const float bm = ok ? __ldg(a.q_mag_f + q) : 0.f;
-            sh->thr[col] = ok ? __ldg(a.topk.thr_f + q) : -__int_as_float(0x7f800000);
-            sh->qm[col] = bm;
-            sh->qs[col] = eps * sqrtf(bm);
+            float4 v = make_float4(-INF, 0.f, INF, 0.f);  // padded query: keep nothing
+            if (q < a.nq) {
+                const float bm = __ldg(a.q_mag_f + q);
+                const float thr = __ldg(a.topk.thr_f + q);
+                const float c = fsn.q_scale ? __ldg(fsn.q_scale + q) : 1.0f;
+                v.x = thr / c;  // -acc*c*rinv <= thr  <=>  -acc*rinv <= thr/c  (c > 0; inf stays inf)
+                if (v.x != v.x) v.x = INF;
+                v.y = -2.0f * c;
+                v.z = METRIC == PKV_L2 ? bm - thr : -thr;  // -inf while there is no threshold
+                if (v.z != v.z) v.z = -INF;
+                v.w = fsn.eps * sqrtf(bm);
+            }
+            sh->qv[col] = v;
         }
     }
     tc::fence_before_sync();
@@ -99,44 +123,49 @@ scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = (int)(a.row_begin + tile * TILE_M);
-                const uint32_t ptile = tile + (uint32_t)prefetch_tiles * gridDim.x;
-                if (prefetch_tiles > 0 && ptile < ntiles)
+                const uint32_t ptile = tile + (uint32_t)fsn.prefetch_tiles * gridDim.x;
+                if (fsn.prefetch_tiles > 0 && ptile < ntiles)
                     for (int kc = 0; kc < kchunks; ++kc)
                         tc::tma_prefetch_2d(&tmap_rows, kc * CHUNK_BYTES, (int)(a.row_begin + ptile * TILE_M));
-                for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->empty[s], ph ^ 1);
                     tc::mbar_expect_tx(&sh->full[s], STAGE);
                     uint8_t *st = smem + (size_t)s * STAGE;
                     tc::tma_load_2d(st, &tmap_rows, &sh->full[s], kc * CHUNK_BYTES, row0);
                     tc::tma_load_2d(st + A_BYTES, &tmap_q, &sh->full[s], kc * CHUNK_BYTES, q0);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc(/*F32*/ 1, /*TF32*/ 2, TILE_M, NQ);
-            uint32_t it = 0, t = 0;
+            constexpr uint32_t idesc = KIND == KIND_TF32 ? tc::make_idesc(/*F32*/ 1, /*TF32*/ 2, TILE_M, NQ)
+                                                         : tc::make_idesc(/*F32*/ 1, /*F16*/ 0, TILE_M, NQ);
+            uint32_t s = 0, ph = 0, t = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
                 const uint32_t buf = t & 1, bph = (t >> 1) & 1;
                 tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
                 tc::fence_after_sync();
                 const uint32_t d_tmem = tmem_base + buf * NQ;
-                for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
                     const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * STAGE);
                     const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
-                        tc::mma_tf32(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
-                                     tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {  // K = 32 bytes per UMMA: 8 tf32 / 16 f16
+                        if (KIND == KIND_TF32)
+                            tc::mma_tf32(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
+                                         tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+                        else
+                            tc::mma_f16(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
+                                        tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
                     }
                     tc::mma_commit(&sh->empty[s]);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
                 tc::mma_commit(&sh->tmem_full[buf]);
             }
@@ -149,8 +178,11 @@ scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
             const uint32_t row = a.row_begin + tile * TILE_M + quarter * 32 + lane;
             const bool row_ok = row < a.row_end;
             const float am = row_ok ? __ldg(a.row_mag_f + row) : 0.f;
+            // rows whose norm is too small for the fp16 image's relative error bound always pass
+            const float bias = (am < fsn.tiny_mag) ? -INF : 0.f;
             const float rinv = rsqrtf(am);
             const float sa2 = 2.0f * sqrtf(am);
+            const float am_b = am + bias;
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NQ;
@@ -159,33 +191,29 @@ scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                 uint32_t v[32];
                 tc::tmem_ld_32x32(taddr + c * 32, v);
                 tc::tmem_ld_wait();
+                // f > 0 <=> the pair cannot be in the top-k; a NaN f is kept (zero-norm rows)
+                unsigned any = 0u;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 th = *reinterpret_cast<const float4 *>(&sh->thr[c * 32 + j]);
-                    const float thv[4] = {th.x, th.y, th.z, th.w};
-                    bool pass[4];
+                for (int j = 0; j < 32; ++j) {
+                    const float acc = __uint_as_float(v[j]);
+                    const float4 qv = sh->qv[c * 32 + j];
+                    float f;
+                    if (METRIC == PKV_COSINE)
+                        f = fmaf(-acc, rinv, bias) - qv.x;                          // -acc*rinv <= thr'
+                    else if (METRIC == PKV_L2)
+                        f = fmaf(acc, qv.y, am_b + qv.z) - sa2 * qv.w;              // |a|^2+|q|^2-2dot-slack <= thr
+                    else
+                        f = fmaf(acc, 0.5f * qv.y, qv.z + bias) - 0.5f * sa2 * qv.w;  // -dot-slack <= thr
+                    v[j] = __float_as_uint(f);
+                    any |= (f > 0.f) ? 0u : 1u;
+                }
+                if (any) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float dot = __uint_as_float(v[j + e]);
-                        float f;
-                        if (METRIC == PKV_COSINE) {
-                            f = -dot * rinv;  // the eps slack is folded into thr (FilterSpec.abs)
-                        } else if (METRIC == PKV_L2) {
-                            // lower bound of the squared distance given |dot~ - dot| <= eps|a||q|
-                            f = fmaf(-2.0f, dot, am + sh->qm[c * 32 + j + e]) - sa2 * sh->qs[c * 32 + j + e];
-                        } else {
-                            f = -dot - 0.5f * sa2 * sh->qs[c * 32 + j + e];
-                        }
-                        pass[e] = !(f > thv[e]);
-                    }
-                    if (pass[0] | pass[1] | pass[2] | pass[3]) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int q = q0 + c * 32 + j + e;
-                            if (pass[e] && row_ok && q < a.nq && topk_member(a.topk, q, row)) {
-                                const uint32_t slot = atomicAdd(pend.cnt + q, 1u);
-                                if (slot < pend.cap) pend.rows[(size_t)q * pend.cap + slot] = row;
-                            }
+                    for (int j = 0; j < 32; ++j) {
+                        const int q = q0 + c * 32 + j;
+                        if (!(__uint_as_float(v[j]) > 0.f) && row_ok && q < a.nq && topk_member(a.topk, q, row)) {
+                            const uint32_t slot = atomicAdd(pend.cnt + q, 1u);
+                            if (slot < pend.cap) pend.rows[(size_t)q * pend.cap + slot] = row;
                         }
                     }
                 }
@@ -201,11 +229,11 @@ scan_f32_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
     if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * NQ);
 }
 
-// Exact re-scoring of the pending (row, query) pairs: one warp per pair, lanes stride the
-// components with the same float4 order and the same xor-reduction tree as scan_f32_simt_kernel.
-template <int METRIC>
-__global__ void __launch_bounds__(256) rescore_f32_kernel(const ScanArgs a, const PendDev pend, SearchStatus *status) {
-    extern __shared__ float4 s_q[];  // one query, dim_pad/4 float4
+// Exact re-scoring of the pending (row, query) pairs from the STORED rows: one warp per pair, lanes
+// stride the components with the same order and the same xor-reduction tree as the CUDA-core scan.
+template <int METRIC, bool ROWS_F16>
+__global__ void __launch_bounds__(256) rescore_kernel(const ScanArgs a, const PendDev pend, SearchStatus *status) {
+    extern __shared__ float4 s_q[];  // one query, dim_pad/4 float4 (f32, widened for an f16 index)
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const int nvec = a.dim_pad >> 2;
@@ -220,28 +248,61 @@ __global__ void __launch_bounds__(256) rescore_f32_kernel(const ScanArgs a, cons
     const float qmag = __ldg(a.q_mag_f + q);
     for (uint32_t e = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += wstride) {
         const uint32_t row = pend.rows[(size_t)q * pend.cap + e];
-        const float4 *rp = (const float4 *)((const uint8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes);
+        const uint8_t *rb = (const uint8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
         float acc = 0.f, nrm = 0.f;
-        for (int j = lane; j < nvec; j += 32) {
-            const float4 av = __ldg(rp + j);
-            const float4 qv = s_q[j];
-            if (METRIC == PKV_L2) {
-                float t;
-                t = av.x - qv.x; acc = fmaf(t, t, acc);
-                t = av.y - qv.y; acc = fmaf(t, t, acc);
-                t = av.z - qv.z; acc = fmaf(t, t, acc);
-                t = av.w - qv.w; acc = fmaf(t, t, acc);
-            } else {
-                acc = fmaf(av.x, qv.x, acc);
-                acc = fmaf(av.y, qv.y, acc);
-                acc = fmaf(av.z, qv.z, acc);
-                acc = fmaf(av.w, qv.w, acc);
+        if (!ROWS_F16) {
+            const float4 *rp = (const float4 *)rb;
+            for (int j = lane; j < nvec; j += 32) {
+                const float4 av = __ldg(rp + j);
+                const float4 qv = s_q[j];
+                if (METRIC == PKV_L2) {
+                    float t;
+                    t = av.x - qv.x; acc = fmaf(t, t, acc);
+                    t = av.y - qv.y; acc = fmaf(t, t, acc);
+                    t = av.z - qv.z; acc = fmaf(t, t, acc);
+                    t = av.w - qv.w; acc = fmaf(t, t, acc);
+                } else {
+                    acc = fmaf(av.x, qv.x, acc);
+                    acc = fmaf(av.y, qv.y, acc);
+                    acc = fmaf(av.z, qv.z, acc);
+                    acc = fmaf(av.w, qv.w, acc);
+                }
+                if (METRIC == PKV_COSINE) {
+                    nrm = fmaf(av.x, av.x, nrm);
+                    nrm = fmaf(av.y, av.y, nrm);
+                    nrm = fmaf(av.z, av.z, nrm);
+                    nrm = fmaf(av.w, av.w, nrm);
+                }
             }
-            if (METRIC == PKV_COSINE) {
-                nrm = fmaf(av.x, av.x, nrm);
-                nrm = fmaf(av.y, av.y, nrm);
-                nrm = fmaf(av.z, av.z, nrm);
-                nrm = fmaf(av.w, av.w, nrm);
+        } else {
+            // same element order as scan_f16_simt_kernel: 8 halfs per lane per step
+            const uint4 *rp = (const uint4 *)rb;
+            const int nvec8 = a.dim_pad >> 3;
+            for (int j = lane; j < nvec8; j += 32) {
+                const uint4 raw8 = __ldg(rp + j);
+                const __half2 *h = reinterpret_cast<const __half2 *>(&raw8);
+                float av[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 p = __half22float2(h[i]);
+                    av[2 * i] = p.x;
+                    av[2 * i + 1] = p.y;
+                }
+                const float4 q0v = s_q[2 * j], q1v = s_q[2 * j + 1];
+                const float qq[8] = {q0v.x, q0v.y, q0v.z, q0v.w, q1v.x, q1v.y, q1v.z, q1v.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (METRIC == PKV_L2) {
+                        const float t = av[i] - qq[i];
+                        acc = fmaf(t, t, acc);
+                    } else {
+                        acc = fmaf(av[i], qq[i], acc);
+                    }
+                }
+                if (METRIC == PKV_COSINE) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) nrm = fmaf(av[i], av[i], nrm);
+                }
             }
         }
 #pragma unroll
@@ -262,92 +323,199 @@ __global__ void __launch_bounds__(256) rescore_f32_kernel(const ScanArgs a, cons
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-template <int NQ, int METRIC>
-int launch_one(const Index &ix, const ScanArgs &a, const PendDev &pend, const CUtensorMap &mrows,
-               const CUtensorMap &mq, int q0, float eps, cudaStream_t s) {
+template <int KIND, int NQ, int METRIC>
+int launch_one(const Index &ix, const ScanArgs &a, const PendDev &pend, const FloatScan &fsn, const CUtensorMap &mrows,
+               const CUtensorMap &mq, int q0, int kchunks, cudaStream_t s) {
     constexpr int STAGE = A_BYTES + NQ * CHUNK_BYTES;
-    const size_t ctrl = sizeof(F32Shared<NQ>);
+    const size_t ctrl = sizeof(FShared<NQ>);
     int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     const size_t smem = 1024 + (size_t)stages * STAGE + ctrl;
-    auto kernel = scan_f32_tc_kernel<NQ, METRIC>;
+    auto kernel = scan_float_tc_kernel<KIND, NQ, METRIC>;
     PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t ntiles = (a.row_end - a.row_begin + TILE_M - 1) / TILE_M;
     const unsigned grid = ntiles < (uint32_t)ix.sm_count ? ntiles : (unsigned)ix.sm_count;
-    kernel<<<grid, TC_THREADS, smem, s>>>(mrows, mq, a, pend, q0, ix.dim_pad * 4 / CHUNK_BYTES, stages, eps,
-                                          ix.opt.tc_prefetch_tiles);
+    kernel<<<grid, TC_THREADS, smem, s>>>(mrows, mq, a, pend, fsn, q0, kchunks, stages);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }
 
-template <int METRIC>
-int launch_metric(const Index &ix, const ScanArgs &a, const PendDev &pend, const CUtensorMap &mrows,
-                  const CUtensorMap &mq128, const CUtensorMap &mq256, float eps, SearchStatus *status, cudaStream_t s,
-                  int *launches) {
+template <int KIND, int METRIC>
+int launch_metric(const Index &ix, const ScanArgs &a, const PendDev &pend, const FloatScan &fsn,
+                  const CUtensorMap &mrows, const CUtensorMap &mq128, const CUtensorMap &mq256, int kchunks,
+                  SearchStatus *status, cudaStream_t s, int *launches) {
     for (int q0 = 0; q0 < a.nq;) {
         const int left = a.nq - q0;
         *launches += 1;
         if (left > 128) {
-            PKV_TRY((launch_one<256, METRIC>(ix, a, pend, mrows, mq256, q0, eps, s)));
+            PKV_TRY((launch_one<KIND, 256, METRIC>(ix, a, pend, fsn, mrows, mq256, q0, kchunks, s)));
             q0 += 256;
         } else {
-            PKV_TRY((launch_one<128, METRIC>(ix, a, pend, mrows, mq128, q0, eps, s)));
+            PKV_TRY((launch_one<KIND, 128, METRIC>(ix, a, pend, fsn, mrows, mq128, q0, kchunks, s)));
             q0 += 128;
         }
     }
-    auto rk = rescore_f32_kernel<METRIC>;
     const size_t smem = (size_t)a.dim_pad * 4;
-    PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ry = (4 * ix.sm_count + a.nq - 1) / a.nq;  // ~4 CTAs per SM in total
     if (ry < 1) ry = 1;
     if (ry > 64) ry = 64;
-    rk<<<dim3((unsigned)a.nq, (unsigned)ry), 256, smem, s>>>(a, pend, status);
+    const dim3 grid((unsigned)a.nq, (unsigned)ry);
+    if (ix.dtype == PKV_F16) {
+        auto rk = rescore_kernel<METRIC, true>;
+        PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rk<<<grid, 256, smem, s>>>(a, pend, status);
+    } else {
+        auto rk = rescore_kernel<METRIC, false>;
+        PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rk<<<grid, 256, smem, s>>>(a, pend, status);
+    }
     PKV_CUDA(cudaGetLastError());
     *launches += 1;
     return PKV_OK;
 }
 
-}  // namespace
-
-int make_tmap_bytes(CUtensorMap *m, const void *base, uint64_t inner_bytes, uint64_t rows, uint64_t pitch_bytes,
-                    uint32_t box_rows);
-
-bool scan_tc_f32_supported(const Index &ix, int nq) {
-    if (ix.dtype != PKV_F32 || ix.opt.force_simt) return false;
-    return nq >= ix.opt.tc_min_queries_f32;
+template <int KIND>
+int launch_kind(const Index &ix, const ScanArgs &a, const PendDev &pend, const FloatScan &fsn, const CUtensorMap &mrows,
+                const CUtensorMap &mq128, const CUtensorMap &mq256, int kchunks, SearchStatus *status, cudaStream_t s,
+                int *launches) {
+    switch (a.metric) {
+        case PKV_COSINE:
+            return launch_metric<KIND, PKV_COSINE>(ix, a, pend, fsn, mrows, mq128, mq256, kchunks, status, s, launches);
+        case PKV_L2:
+            return launch_metric<KIND, PKV_L2>(ix, a, pend, fsn, mrows, mq128, mq256, kchunks, status, s, launches);
+        default:
+            return launch_metric<KIND, PKV_DOT>(ix, a, pend, fsn, mrows, mq128, mq256, kchunks, status, s, launches);
+    }
 }
+
+// ---- fp16 image helpers ----
+// q16[q] = half(q * 2^e_q) with 2^e_q the power of two that puts |q|_inf * 2^e_q in [4096, 8192);
+// q_scale[q] = 1 / (row_scale * 2^e_q) turns an accumulator into the true dot product.
+__global__ void prep_queries_f16_kernel(const float *q, int dim, int dim_pad, int dim_pad_h, float row_scale,
+                                        __half *q16, float *q_scale) {
+    const int qi = blockIdx.x;
+    __shared__ float s_max[32];
+    const float *src = q + (size_t)qi * dim_pad;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        const float v = fabsf(src[i]);
+        if (v > m && v < __int_as_float(0x7f800000)) m = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? s_max[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) s_max[0] = m;
+    }
+    __syncthreads();
+    m = s_max[0];
+    int e = 0;
+    if (m > 0.f) {
+        e = 13 - (ilogbf(m) + 1);
+        if (e > 100) e = 100;
+        if (e < -100) e = -100;
+    }
+    const float qs = ldexpf(1.0f, e);
+    for (int i = threadIdx.x; i < dim_pad_h; i += blockDim.x)
+        q16[(size_t)qi * dim_pad_h + i] = __float2half_rn(i < dim ? src[i] * qs : 0.f);
+    if (threadIdx.x == 0) q_scale[qi] = 1.0f / (row_scale * qs);
+}
+
+__global__ void shadow_convert_kernel(const float *rows, int64_t pitch_f, int dim, int dim_pad_h, float scale,
+                                      int64_t row_begin, int64_t row_end, __half *out) {
+    const int64_t total = (row_end - row_begin) * dim_pad_h;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = row_begin + i / dim_pad_h;
+        const int c = (int)(i % dim_pad_h);
+        out[r * dim_pad_h + c] = __float2half_rn(c < dim ? rows[r * pitch_f + c] * scale : 0.f);
+    }
+}
+
+}  // namespace
 
 // TF32 keeps 10 explicit mantissa bits; whether the tensor core truncates or rounds the f32
 // operands, each is off by < 2^-10 relative, a product by < 2^-9, so
-// |dot~ - dot| <= 2^-9 * sum|a_i q_i| <= 2^-9 |a||q| (Cauchy-Schwarz); the f32 accumulation adds
-// ~1e-6.  2.2e-3 > 2^-9 = 1.953e-3 leaves margin.  tests/test_gpu_tc_f32.py measures the real error.
+// |dot~ - dot| <= 2^-9 * sum|a_i q_i| <= 2^-9 |a||q| (Cauchy-Schwarz); f32 accumulation adds ~1e-6.
 static constexpr float TF32_EPS = 2.2e-3f;
+// fp16 image, round-to-nearest of power-of-two-scaled values: each normal operand is off by <= 2^-11
+// relative, a product by < 2^-10 (9.8e-4); components that fall into the fp16 subnormal range add
+// at most 2^-25*sqrt(D)/(scale*|a|) relative, < 2^-13 for every row that is not flagged "tiny"
+// (those are always re-scored); queries are scaled per query so the same holds for them.
+static constexpr float F16_SHADOW_EPS = 1.25e-3f;
+// true f16 index: operands are exact, products are exact in f32, only the accumulation rounds
+static constexpr float F16_EXACT_EPS = 2.0e-4f;
 
-FilterSpec filter_spec_tc_f32(int metric) {
+bool scan_tc_f32_supported(const Index &ix, int nq) {
+    if (ix.opt.force_simt) return false;
+    if (ix.dtype == PKV_F32 || ix.dtype == PKV_F16) return nq >= ix.opt.tc_min_queries_f32;
+    return false;
+}
+
+static bool use_shadow(const Index &ix) { return ix.dtype == PKV_F32 && ix.d_shadow && ix.opt.use_shadow; }
+
+static float float_eps(const Index &ix) {
+    if (ix.dtype == PKV_F16) return F16_EXACT_EPS;
+    return use_shadow(ix) ? F16_SHADOW_EPS : TF32_EPS;
+}
+
+FilterSpec filter_spec_tc_f32(const Index &ix, int metric) {
     FilterSpec fs = filter_spec_simt(PKV_F32, metric);
-    if (metric == PKV_COSINE) fs.abs = TF32_EPS;  // in units of dot/|a|: scaled by |q| in filter_threshold
+    if (metric == PKV_COSINE) fs.abs = float_eps(ix);  // in units of dot/|a|: scaled by |q| in filter_threshold
     return fs;  // L2 / DOT apply the per-row bound inside the kernel
 }
 
-int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, uint32_t *d_pend_rows, uint32_t *d_pend_cnt, uint32_t pend_cap,
-                       SearchStatus *d_status, cudaStream_t s, int *launches) {
+int scan_tc_f32_kind(const Index &ix) { return ix.dtype == PKV_F16 ? 6 : (use_shadow(ix) ? 7 : 4); }
+
+int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) {
+    if (row_end <= row_begin) return PKV_OK;
+    const int64_t total = (row_end - row_begin) * ix.dim_pad_h;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    shadow_convert_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float *)ix.d_data, ix.pitch / 4, ix.dim, ix.dim_pad_h,
+                                                          ix.shadow_scale, row_begin, row_end, ix.d_shadow);
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
+int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
     if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
-    PendDev pend{d_pend_rows, d_pend_cnt, pend_cap};
-    PKV_CUDA(cudaMemsetAsync(d_pend_cnt, 0, sizeof(uint32_t) * a.nq, s));
+    PendDev pend{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.cap};
+    PKV_CUDA(cudaMemsetAsync(ws.d_pend_cnt, 0, sizeof(uint32_t) * a.nq, s));
+    FloatScan fsn;
+    fsn.eps = float_eps(ix);
+    fsn.prefetch_tiles = ix.opt.tc_prefetch_tiles;
+    fsn.q_scale = nullptr;
+    fsn.tiny_mag = 0.f;
     CUtensorMap mrows, mq128, mq256;
-    PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.pitch, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
-    PKV_TRY(make_tmap_bytes(&mq128, a.queries, (uint64_t)ix.pitch, (uint64_t)a.nq, (uint64_t)ix.pitch, 128));
-    PKV_TRY(make_tmap_bytes(&mq256, a.queries, (uint64_t)ix.pitch, (uint64_t)a.nq, (uint64_t)ix.pitch, 256));
-    switch (a.metric) {
-        case PKV_COSINE:
-            return launch_metric<PKV_COSINE>(ix, a, pend, mrows, mq128, mq256, TF32_EPS, d_status, s, launches);
-        case PKV_L2: return launch_metric<PKV_L2>(ix, a, pend, mrows, mq128, mq256, TF32_EPS, d_status, s, launches);
-        default: return launch_metric<PKV_DOT>(ix, a, pend, mrows, mq128, mq256, TF32_EPS, d_status, s, launches);
+    const bool shadow = use_shadow(ix);
+    if (ix.dtype == PKV_F32 && !shadow) {
+        PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.pitch, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
+        PKV_TRY(make_tmap_bytes(&mq128, a.queries, (uint64_t)ix.pitch, (uint64_t)a.nq, (uint64_t)ix.pitch, 128));
+        PKV_TRY(make_tmap_bytes(&mq256, a.queries, (uint64_t)ix.pitch, (uint64_t)a.nq, (uint64_t)ix.pitch, 256));
+        return launch_kind<KIND_TF32>(ix, a, pend, fsn, mrows, mq128, mq256, (int)(ix.pitch / CHUNK_BYTES), ws.d_status, s,
+                                      launches);
     }
+    // fp16 image: the shadow of an f32 index, or the rows of an f16 index
+    const uint64_t pitch_h = (uint64_t)ix.dim_pad_h * 2;
+    const void *img = shadow ? (const void *)ix.d_shadow : (const void *)ix.d_data;
+    const float row_scale = shadow ? ix.shadow_scale : 1.0f;
+    prep_queries_f16_kernel<<<a.nq, 128, 0, s>>>((const float *)a.queries, ix.dim, ix.dim_pad, ix.dim_pad_h, row_scale,
+                                                 ws.d_q16, ws.d_q_scale);
+    PKV_CUDA(cudaGetLastError());
+    *launches += 1;
+    fsn.q_scale = ws.d_q_scale;
+    if (shadow) {
+        // |a| * scale below sqrt(D) * 2^-12: components sit in or near the fp16 subnormal range
+        const float lim = sqrtf((float)ix.dim) * 0.000244140625f / ix.shadow_scale;
+        fsn.tiny_mag = lim * lim;
+    }
+    PKV_TRY(make_tmap_bytes(&mrows, img, pitch_h, (uint64_t)ix.sealed_rows, pitch_h, TILE_M));
+    PKV_TRY(make_tmap_bytes(&mq128, ws.d_q16, pitch_h, (uint64_t)a.nq, pitch_h, 128));
+    PKV_TRY(make_tmap_bytes(&mq256, ws.d_q16, pitch_h, (uint64_t)a.nq, pitch_h, 256));
+    return launch_kind<KIND_F16>(ix, a, pend, fsn, mrows, mq128, mq256, (int)(pitch_h / CHUNK_BYTES), ws.d_status, s,
+                                 launches);
 }
 
 }  // namespace pkv

@@ -6,6 +6,11 @@
 #include "pkv_device.cuh"
 
 namespace pkv {
+
+// 2-D TMA map over a row-major byte matrix, box = 128 B x box_rows, SWIZZLE_128B (pkv_scan_tc.cu)
+int make_tmap_bytes(CUtensorMap *m, const void *base, uint64_t inner_bytes, uint64_t rows, uint64_t pitch_bytes,
+                    uint32_t box_rows);
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,7 +140,9 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default (release.cta) semantics: the consumer is the MMA issuer, ordered by tcgen05 fences, not by
+    // generic-proxy memory; a cluster-scope release would cost a MEMBAR per tile per warp
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into this CTA's smem, completion bytes credited to the mbarrier at cluster address `bar`
 __device__ __forceinline__ void tma_load_2d_cta2(void *smem_dst, const CUtensorMap *tmap, uint32_t bar_cluster_addr,

