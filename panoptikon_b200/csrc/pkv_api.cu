@@ -72,6 +72,8 @@ Workspace::~Workspace() {
     cudaFree(d_bitmap);
     for (auto &e : ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : chunk_ev)
+        if (e) cudaEventDestroy(e);
     if (owns_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -172,13 +174,25 @@ struct SearchRun {
     int launches = 0, scan_launches = 0;
     int depth_overflows = 0;
     bool use_tc = false, use_tc_f32 = false;
+    int unsynced = 0;  // chunks enqueued since the last host sync
 };
 
-static int scan_range(SearchRun &r, int64_t b, int64_t e) {
+static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
     r.args.row_begin = (uint32_t)b;
     r.args.row_end = (uint32_t)e;
     const bool timed = r.ix.opt.time_kernels != 0;
-    if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[0], r.s));
+    cudaEvent_t ev_begin = r.ws.ev[0], ev_end = r.ws.ev[1];
+    if (!sync && timed) {
+        // chunks enqueued back to back keep their own event pair; read after the final sync
+        while (r.ws.chunk_ev.size() < (size_t)(2 * (r.unsynced + 1))) {
+            cudaEvent_t ev = nullptr;
+            PKV_CUDA(cudaEventCreate(&ev));
+            r.ws.chunk_ev.push_back(ev);
+        }
+        ev_begin = r.ws.chunk_ev[2 * r.unsynced];
+        ev_end = r.ws.chunk_ev[2 * r.unsynced + 1];
+    }
+    if (timed) PKV_CUDA(cudaEventRecord(ev_begin, r.s));
     int n = 0;
     PKV_TRY(launch_reset_status(r.ws, r.s));
     // While some query has no threshold yet every pair is a candidate: that is dense work with one
@@ -193,9 +207,13 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e) {
         PKV_TRY(launch_scan_simt(r.ix, r.args, r.s, &n));
     r.launches += n;
     r.scan_launches += n;
-    if (timed) PKV_CUDA(cudaEventRecord(r.ws.ev[1], r.s));
+    if (timed) PKV_CUDA(cudaEventRecord(ev_end, r.s));
     PKV_TRY(launch_select(r.ix, r.ws, r.nq, r.k, r.args.metric, r.fs, r.s));
     r.launches += 2;
+    if (!sync) {
+        r.unsynced++;
+        return PKV_OK;
+    }
     PKV_CUDA(cudaMemcpyAsync(r.ws.h_status, r.ws.d_status, sizeof(SearchStatus), cudaMemcpyDeviceToHost, r.s));
     PKV_CUDA(cudaStreamSynchronize(r.s));
     if (timed) {
@@ -269,11 +287,23 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // Chunk schedule: the first chunk (no threshold yet: every row is a candidate) is sized
     // so it cannot overflow; afterwards a chunk of c rows behind `seen` scanned rows yields
     // about k*c/seen candidates per query, so chunks grow geometrically.
+    // (candidate work per chunk grows with the growth factor, chunk count shrinks with its log:
+    // ~4x measured best on B200 for k=100)
     double growth = (double)(ws.cap - k) / (3.0 * k);
+    if (growth > 4.0) growth = 4.0;
     if (ix.opt.chunk_growth_x100 > 0) growth = ix.opt.chunk_growth_x100 / 100.0;
     if (growth < 0.25) growth = 0.25;
+    // Optimistic mode: once every query has a threshold (after the first chunk) the remaining chunks
+    // and their selects are enqueued back to back with no host round trip; the sticky overflow flag
+    // is checked once at the end and, if it ever fired, the search is redone with a sync per chunk
+    // (which is what splits overflowing ranges).  Bitmap searches stay careful: their candidate
+    // rate is unknown until the first members are seen.
+    static const bool trace_env = getenv("PKV_TRACE") != nullptr;
+    bool optimistic = ix.opt.optimistic && !d_bitmap && !trace_env;
+restart:
     int64_t pos = 0;
     r.min_filled = 0;
+    r.unsynced = 0;
     while (pos < N) {
         int64_t chunk;
         if (r.min_filled < (uint32_t)k) {
@@ -287,8 +317,26 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
         if (chunk >= 1024) chunk = chunk / 128 * 128;
         if (chunk > N - pos) chunk = N - pos;
         if (chunk < 1) chunk = 1;
-        PKV_TRY(scan_range(r, pos, pos + chunk));
+        const bool sync = !(optimistic && r.min_filled >= (uint32_t)k && pos > 0);
+        PKV_TRY(scan_range(r, pos, pos + chunk, sync));
         pos += chunk;
+    }
+    if (r.unsynced > 0) {
+        PKV_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(SearchStatus), cudaMemcpyDeviceToHost, s));
+        PKV_CUDA(cudaStreamSynchronize(s));
+        if (ix.opt.time_kernels) {
+            for (int i = 0; i < r.unsynced; ++i) {
+                float ms = 0.f;
+                PKV_CUDA(cudaEventElapsedTime(&ms, ws.chunk_ev[2 * i], ws.chunk_ev[2 * i + 1]));
+                r.scan_ms += ms;
+            }
+        }
+        if (ws.h_status->sticky_overflow) {
+            r.depth_overflows++;
+            optimistic = false;
+            PKV_TRY(launch_reset_state(ws, nq, s));
+            goto restart;
+        }
     }
     PKV_TRY(launch_finalize(ix, ws, nq, k, d_ids, d_dist, d_counts, s));
     r.launches += 1;
@@ -793,6 +841,7 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "tc_cta2")) ix.opt.tc_cta2 = (int)value;
     else if (!strcmp(name, "use_shadow")) ix.opt.use_shadow = (int)value;
     else if (!strcmp(name, "simt_bootstrap")) ix.opt.simt_bootstrap = (int)value;
+    else if (!strcmp(name, "optimistic")) ix.opt.optimistic = (int)value;
     else if (!strcmp(name, "tc_min_queries_f32")) ix.opt.tc_min_queries_f32 = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;

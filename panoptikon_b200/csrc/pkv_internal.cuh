@@ -132,7 +132,7 @@ struct SearchStatus {  // device -> pinned host after every chunk
     uint32_t max_raw_cnt;
     uint32_t any_overflow;
     uint32_t min_filled;
-    uint32_t pad;
+    uint32_t sticky_overflow;  // like any_overflow but only cleared at the start of a search
 };
 
 // --------------------------------------------------------------- host side
@@ -163,6 +163,7 @@ struct Workspace {
     size_t bitmap_bytes = 0;
     size_t out_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> chunk_ev;  // begin/end pairs for chunks enqueued without a host sync
     ~Workspace();
 };
 
@@ -173,6 +174,7 @@ struct Options {
     int64_t chunk_growth_x100 = 0;   // 0 = auto
     int time_kernels = 1;
     int tc_min_queries_f32 = 17;     // f32: the FFMA kernel is HBM-bound up to ~16 queries
+    int optimistic = 1;              // enqueue all chunks after the first without host syncs; verify at the end
     int simt_bootstrap = 1;          // threshold-less first chunk runs on the CUDA-core kernel
     int use_shadow = 1;              // f32 index: keep a scaled fp16 image for the tensor-core filter
     int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA

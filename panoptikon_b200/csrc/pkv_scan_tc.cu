@@ -12,7 +12,7 @@
 //   warp 1      owns TMEM; one elected lane issues tcgen05.mma (M=128 rows, N=128 queries,
 //               K=32 per instruction) against the query tile that stays resident in shared memory,
 //               and tcgen05.commit's stage release / accumulator-ready barriers
-//   warps 2..5  epilogue: tcgen05.ld the 128x128 s32 accumulator (double-buffered in TMEM, so the
+//   warps 2..17 epilogue: tcgen05.ld the 128x128 s32 accumulator (double-buffered in TMEM, so the
 //               next tile's MMAs overlap), integer pre-filter against a per-(warp,query) bound,
 //               exact filter, exact key, candidate push
 //
@@ -30,13 +30,13 @@ constexpr int CHUNK_BYTES = 128;    // K bytes per stage row (one swizzle atom)
 constexpr int STAGE_BYTES = TILE_M * CHUNK_BYTES;  // 16 KiB
 constexpr int QCHUNK_BYTES = TILE_N * CHUNK_BYTES;
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_WARPS = 8;        // two warps per TMEM lane quarter, 64 columns each
+constexpr int EPI_WARPS = 16;       // four warps per TMEM lane quarter, 32 columns each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 2 * TILE_N;  // double-buffered accumulator
-constexpr int COLS_PER_WARP = TILE_N / 2;
-constexpr int HOLD_CAP = 160;       // staged pre-filter survivors per epilogue warp
-constexpr int HOLD_FLUSH = 96;      // flush (lane-parallel) once this many are parked
+constexpr int COLS_PER_WARP = TILE_N / 4;
+constexpr int HOLD_CAP = 64;        // staged pre-filter survivors per epilogue warp
+constexpr int HOLD_FLUSH = 32;      // flush (lane-parallel) once this many are parked
 
 struct TcShared {  // control block behind the data stages
     uint64_t full[MAX_STAGES];
@@ -202,8 +202,7 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         // ===================== epilogue =====================
         const int ew = warp - 2;           // 0..7
         const int quarter = warp & 3;      // TMEM lane quarter this warp may access
-        const int half = ew >> 2;          // which 64 columns
-        const int col0 = half * COLS_PER_WARP;
+        const int col0 = (ew >> 2) * COLS_PER_WARP;  // which 32 columns
         uint32_t t = 0;
         uint32_t row = a.row_begin + blockIdx.x * TILE_M + quarter * 32 + lane;
         int am = (blockIdx.x < ntiles && row < a.row_end) ? __ldg(a.row_mag_i + row) : -1;
@@ -237,7 +236,7 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int4 b = *reinterpret_cast<const int4 *>(&sh->bound[ew][c * 32 + j]);
-                    any |= (b.x + ~(int)v[j]) | (b.y + ~(int)v[j + 1]) | (b.z + ~(int)v[j + 2]) | (b.w + ~(int)v[j + 3]);
+                    any |= (b.x - (int)v[j] - 1) | (b.y - (int)v[j + 1] - 1) | (b.z - (int)v[j + 2] - 1) | (b.w - (int)v[j + 3] - 1);
                 }
                 if (any < 0) {
 #pragma unroll

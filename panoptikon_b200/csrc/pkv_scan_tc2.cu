@@ -11,7 +11,7 @@
 //                        the multicast commits; both CTAs run a TMA producer and 8 epilogue warps.
 //   full[s]      lives in the leader, completed by BOTH CTAs' TMA loads (cta_group::2 form)
 //   empty[s], tmem_full[b]  exist in both CTAs, arrived by tcgen05.commit ... multicast::cluster
-//   tmem_empty[b] lives in the leader, 16 arrivals (8 epilogue warps x 2 CTAs, remote via mapa)
+//   tmem_empty[b] lives in the leader, 32 arrivals (16 epilogue warps x 2 CTAs, remote via mapa)
 #include "pkv_tc.cuh"
 
 namespace pkv {
@@ -26,13 +26,13 @@ constexpr int CHUNK_BYTES = 128;
 constexpr int STAGE_BYTES = ROWS_PER_CTA * CHUNK_BYTES;
 constexpr int QCHUNK_BYTES = QN_CTA * CHUNK_BYTES;
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;  // four per TMEM lane quarter, 64 columns each: enough warps per scheduler to hide TMEM-load latency
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 2 * QN;  // double-buffered 128 x 256 accumulator: the whole TMEM
-constexpr int COLS_PER_WARP = QN / 2;
-constexpr int HOLD_CAP = 160;    // staged pre-filter survivors per epilogue warp
-constexpr int HOLD_FLUSH = 96;   // flush (lane-parallel) once this many are parked
+constexpr int COLS_PER_WARP = QN / 4;
+constexpr int HOLD_CAP = 64;     // staged pre-filter survivors per epilogue warp
+constexpr int HOLD_FLUSH = 32;   // flush (lane-parallel) once this many are parked
 
 struct Tc2Shared {
     uint64_t full[MAX_STAGES];
@@ -158,11 +158,6 @@ scan_i8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
             uint32_t s = 0, ph = 0;
             for (uint32_t tile = pair; tile < ntiles; tile += npairs) {
                 const int row0 = (int)(a.row_begin + tile * TILE_ROWS + rank * ROWS_PER_CTA);
-                const uint32_t ptile = tile + (uint32_t)prefetch_tiles * npairs;
-                if (prefetch_tiles > 0 && ptile < ntiles)
-                    for (int kc = 0; kc < kchunks; ++kc)
-                        tc::tma_prefetch_2d(&tmap_rows, kc * CHUNK_BYTES,
-                                            (int)(a.row_begin + ptile * TILE_ROWS + rank * ROWS_PER_CTA));
                 for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->empty[s], ph ^ 1);
                     if (rank == 0) tc::mbar_expect_tx(&sh->full[s], 2 * STAGE_BYTES);  // both CTAs' bytes
@@ -236,7 +231,7 @@ scan_i8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int4 b = *reinterpret_cast<const int4 *>(&sh->bound[ew][c * 32 + j]);
-                    any |= (b.x + ~(int)v[j]) | (b.y + ~(int)v[j + 1]) | (b.z + ~(int)v[j + 2]) | (b.w + ~(int)v[j + 3]);
+                    any |= (b.x - (int)v[j] - 1) | (b.y - (int)v[j + 1] - 1) | (b.z - (int)v[j + 2] - 1) | (b.w - (int)v[j + 3] - 1);
                 }
                 if (any < 0) {
 #pragma unroll

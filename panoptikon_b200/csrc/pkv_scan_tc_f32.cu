@@ -46,9 +46,13 @@ struct FShared {
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    // per query: x = threshold in accumulator units (cosine), y = -2*c (c: accumulator -> true dot),
-    //            z = |q|^2 - thr_f (L2) or -thr_f (DOT), w = eps*|q|
-    alignas(16) float4 qv[NQ];
+    // per query (structure of arrays so that one 128-bit load serves four queries):
+    //   qx = threshold in accumulator units (cosine), qy = -2*c (c: accumulator -> true dot),
+    //   qz = |q|^2 - thr_f (L2) or -thr_f (DOT), qw = eps*|q|
+    alignas(16) float qx[NQ];
+    alignas(16) float qy[NQ];
+    alignas(16) float qz[NQ];
+    alignas(16) float qw[NQ];
 };
 
 struct PendDev {
@@ -63,6 +67,57 @@ struct FloatScan {
     float tiny_mag;        // rows with |a|^2 below this always go to re-scoring (fp16 image underflow)
     int prefetch_tiles;
 };
+
+
+// Thresholds one 32-column chunk of the accumulator (thread = row).  t >= 0 (or NaN) <=> the pair
+// may be in the top-k; the sign bits are AND-ed so that the common "nothing passes" case costs
+// ~2 instructions per element and one branch per 32.
+template <int METRIC, int NQ>
+__device__ __forceinline__ void threshold_chunk(uint32_t (&v)[32], const FShared<NQ> *sh, int cbase, float rinv,
+                                                float bias, float am_b, float sa2, const ScanArgs &a,
+                                                const PendDev &pend, int q0, uint32_t row, bool row_ok) {
+    unsigned allneg = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 x4 = *reinterpret_cast<const float4 *>(&sh->qx[cbase + j]);
+        float t[4];
+        if (METRIC == PKV_COSINE) {
+            // -acc*rinv + bias <= thr'  <=>  acc*rinv + (thr' - bias) >= 0
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t[e] = fmaf(__uint_as_float(v[j + e]), rinv, xs[e] - bias);
+        } else {
+            const float4 y4 = *reinterpret_cast<const float4 *>(&sh->qy[cbase + j]);
+            const float4 z4 = *reinterpret_cast<const float4 *>(&sh->qz[cbase + j]);
+            const float4 w4 = *reinterpret_cast<const float4 *>(&sh->qw[cbase + j]);
+            const float ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w},
+                        ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float acc = __uint_as_float(v[j + e]);
+                if (METRIC == PKV_L2)  // |a|^2 + |q|^2 - 2 dot - slack <= thr
+                    t[e] = sa2 * ws[e] - fmaf(acc, ys[e], am_b + zs[e]);
+                else  // -dot - slack <= thr
+                    t[e] = 0.5f * sa2 * ws[e] - fmaf(acc, 0.5f * ys[e], zs[e] + bias);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[j + e] = __float_as_uint(t[e]);
+            allneg &= v[j + e];
+        }
+    }
+    if ((int)allneg >= 0) {  // some element has its sign bit clear
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int q = q0 + cbase + j;
+            if (!(__uint_as_float(v[j]) < 0.f) && row_ok && q < a.nq && topk_member(a.topk, q, row)) {
+                const uint32_t slot = atomicAdd(pend.cnt + q, 1u);
+                if (slot < pend.cap) pend.rows[(size_t)q * pend.cap + slot] = row;
+            }
+        }
+    }
+}
 
 template <int KIND, int NQ, int METRIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -113,7 +168,10 @@ scan_float_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid
                 if (v.z != v.z) v.z = -INF;
                 v.w = fsn.eps * sqrtf(bm);
             }
-            sh->qv[col] = v;
+            sh->qx[col] = v.x;
+            sh->qy[col] = v.y;
+            sh->qz[col] = v.z;
+            sh->qw[col] = v.w;
         }
     }
     tc::fence_before_sync();
@@ -191,32 +249,7 @@ scan_float_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid
                 uint32_t v[32];
                 tc::tmem_ld_32x32(taddr + c * 32, v);
                 tc::tmem_ld_wait();
-                // f > 0 <=> the pair cannot be in the top-k; a NaN f is kept (zero-norm rows)
-                unsigned any = 0u;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float acc = __uint_as_float(v[j]);
-                    const float4 qv = sh->qv[c * 32 + j];
-                    float f;
-                    if (METRIC == PKV_COSINE)
-                        f = fmaf(-acc, rinv, bias) - qv.x;                          // -acc*rinv <= thr'
-                    else if (METRIC == PKV_L2)
-                        f = fmaf(acc, qv.y, am_b + qv.z) - sa2 * qv.w;              // |a|^2+|q|^2-2dot-slack <= thr
-                    else
-                        f = fmaf(acc, 0.5f * qv.y, qv.z + bias) - 0.5f * sa2 * qv.w;  // -dot-slack <= thr
-                    v[j] = __float_as_uint(f);
-                    any |= (f > 0.f) ? 0u : 1u;
-                }
-                if (any) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int q = q0 + c * 32 + j;
-                        if (!(__uint_as_float(v[j]) > 0.f) && row_ok && q < a.nq && topk_member(a.topk, q, row)) {
-                            const uint32_t slot = atomicAdd(pend.cnt + q, 1u);
-                            if (slot < pend.cap) pend.rows[(size_t)q * pend.cap + slot] = row;
-                        }
-                    }
-                }
+                threshold_chunk<METRIC, NQ>(v, sh, c * 32, rinv, bias, am_b, sa2, a, pend, q0, row, row_ok);
             }
             tc::fence_before_sync();
             __syncwarp();
@@ -229,6 +262,161 @@ scan_float_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid
     if (warp == 1) tc::tmem_dealloc(tmem_base, 2 * NQ);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-CTA (cta_group::2) variant for 256 queries per pass: M=256 rows x N=256 queries per UMMA; each
+// CTA of the pair streams its own 128 rows AND its own 128-query half of every K-chunk, so the
+// per-SM L2->smem traffic per corpus byte is halved versus the 1-CTA kernel (which is L2-bound at
+// NQ=256).  Barrier topology as in pkv_scan_tc2.cu.
+constexpr int P_EPI_WARPS = 16;
+constexpr int P_THREADS = 64 + P_EPI_WARPS * 32;
+constexpr int P_NQ = 256;
+constexpr int P_STAGE = A_BYTES + 128 * CHUNK_BYTES;  // 16 KB rows + 16 KB query half per CTA
+
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(P_THREADS, 1)
+scan_float_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
+                      const ScanArgs a, const PendDev pend, const FloatScan fsn, const int q0, const int kchunks,
+                      const int stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = tc::smem_u32(smem_raw);
+    uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    FShared<P_NQ> *sh = reinterpret_cast<FShared<P_NQ> *>(smem + (size_t)stages * P_STAGE);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const uint32_t nrows = a.row_end - a.row_begin;
+    const uint32_t ntiles = (nrows + 2 * TILE_M - 1) / (2 * TILE_M);
+    const float INF = __int_as_float(0x7f800000);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            tc::mbar_init(&sh->full[s], 1);
+            tc::mbar_init(&sh->empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&sh->tmem_full[b], 1);
+            tc::mbar_init(&sh->tmem_empty[b], 2 * P_EPI_WARPS);
+        }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmap_rows);
+        tc::prefetch_tmap(&tmap_q);
+    }
+    if (warp == 1) {
+        tc::tmem_alloc_cta2(&sh->tmem_base, 2 * P_NQ);
+        tc::tmem_relinquish_cta2();
+    }
+    if (warp >= 2) {
+        for (int col = threadIdx.x - 64; col < P_NQ; col += P_EPI_WARPS * 32) {
+            const int q = q0 + col;
+            float4 v = make_float4(-INF, 0.f, INF, 0.f);
+            if (q < a.nq) {
+                const float bm = __ldg(a.q_mag_f + q);
+                const float thr = __ldg(a.topk.thr_f + q);
+                const float c = fsn.q_scale ? __ldg(fsn.q_scale + q) : 1.0f;
+                v.x = thr / c;
+                if (v.x != v.x) v.x = INF;
+                v.y = -2.0f * c;
+                v.z = METRIC == PKV_L2 ? bm - thr : -thr;
+                if (v.z != v.z) v.z = -INF;
+                v.w = fsn.eps * sqrtf(bm);
+            }
+            sh->qx[col] = v.x;
+            sh->qy[col] = v.y;
+            sh->qz[col] = v.z;
+            sh->qw[col] = v.w;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t tile = pair; tile < ntiles; tile += npairs) {
+                const int row0 = (int)(a.row_begin + tile * 2 * TILE_M + rank * TILE_M);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    tc::mbar_wait(&sh->empty[s], ph ^ 1);
+                    if (rank == 0) tc::mbar_expect_tx(&sh->full[s], 2 * P_STAGE);
+                    const uint32_t full0 = tc::mapa(tc::smem_u32(&sh->full[s]), 0);
+                    uint8_t *st = smem + (size_t)s * P_STAGE;
+                    tc::tma_load_2d_cta2(st, &tmap_rows, full0, kc * CHUNK_BYTES, row0);
+                    tc::tma_load_2d_cta2(st + A_BYTES, &tmap_q, full0, kc * CHUNK_BYTES, q0 + (int)rank * 128);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = KIND == KIND_TF32 ? tc::make_idesc(/*F32*/ 1, /*TF32*/ 2, 2 * TILE_M, P_NQ)
+                                                         : tc::make_idesc(/*F32*/ 1, /*F16*/ 0, 2 * TILE_M, P_NQ);
+            uint32_t s = 0, ph = 0, t = 0;
+            for (uint32_t tile = pair; tile < ntiles; tile += npairs, ++t) {
+                const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+                tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * P_NQ;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    tc::mbar_wait(&sh->full[s], ph);
+                    tc::fence_after_sync();
+                    const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * P_STAGE);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
+                        if (KIND == KIND_TF32)
+                            tc::mma_tf32_cta2(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
+                                              tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+                        else
+                            tc::mma_f16_cta2(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
+                                             tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+                    }
+                    tc::mma_commit_cta2(&sh->empty[s]);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+                }
+                tc::mma_commit_cta2(&sh->tmem_full[buf]);
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int col0 = (ew >> 2) * (P_NQ / 4);
+        const uint32_t empty0 = tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0);
+        const uint32_t empty1 = tc::mapa(tc::smem_u32(&sh->tmem_empty[1]), 0);
+        uint32_t t = 0;
+        for (uint32_t tile = pair; tile < ntiles; tile += npairs, ++t) {
+            const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            const uint32_t row = a.row_begin + tile * 2 * TILE_M + rank * TILE_M + quarter * 32 + lane;
+            const bool row_ok = row < a.row_end;
+            const float am = row_ok ? __ldg(a.row_mag_f + row) : 0.f;
+            const float bias = (am < fsn.tiny_mag) ? -INF : 0.f;
+            const float rinv = rsqrtf(am);
+            const float sa2 = 2.0f * sqrtf(am);
+            const float am_b = am + bias;
+            tc::mbar_wait(&sh->tmem_full[buf], bph);
+            tc::fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * P_NQ + col0;
+#pragma unroll 1
+            for (int c = 0; c < P_NQ / 4 / 32; ++c) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(taddr + c * 32, v);
+                tc::tmem_ld_wait();
+                threshold_chunk<METRIC, P_NQ>(v, sh, col0 + c * 32, rinv, bias, am_b, sa2, a, pend, q0, row, row_ok);
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(buf ? empty1 : empty0);
+        }
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync();
+    if (warp == 1) tc::tmem_dealloc_cta2(tmem_base, 2 * P_NQ);
+}
+
 // Exact re-scoring of the pending (row, query) pairs from the STORED rows: one warp per pair, lanes
 // stride the components with the same order and the same xor-reduction tree as the CUDA-core scan.
 template <int METRIC, bool ROWS_F16>
@@ -239,7 +427,10 @@ __global__ void __launch_bounds__(256) rescore_kernel(const ScanArgs a, const Pe
     const int nvec = a.dim_pad >> 2;
     const uint32_t raw = pend.cnt[q];
     const uint32_t n = raw < pend.cap ? raw : pend.cap;
-    if (blockIdx.y == 0 && threadIdx.x == 0 && raw > pend.cap) atomicOr(&status->any_overflow, 1u);
+    if (blockIdx.y == 0 && threadIdx.x == 0 && raw > pend.cap) {
+        atomicOr(&status->any_overflow, 1u);
+        atomicOr(&status->sticky_overflow, 1u);
+    }
     if (n == 0) return;
     const float4 *gq = (const float4 *)a.queries + (size_t)q * nvec;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) s_q[i] = gq[i];
@@ -341,13 +532,44 @@ int launch_one(const Index &ix, const ScanArgs &a, const PendDev &pend, const Fl
 }
 
 template <int KIND, int METRIC>
+int launch_pair(const Index &ix, const ScanArgs &a, const PendDev &pend, const FloatScan &fsn, const CUtensorMap &mrows,
+                const CUtensorMap &mq128, int q0, int kchunks, cudaStream_t s) {
+    const size_t ctrl = sizeof(FShared<P_NQ>);
+    int stages = (int)((227 * 1024 - 1024 - ctrl) / P_STAGE);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    const size_t smem = 1024 + (size_t)stages * P_STAGE + ctrl;
+    auto kernel = scan_float_tc2_kernel<KIND, METRIC>;
+    PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t ntiles = (a.row_end - a.row_begin + 2 * TILE_M - 1) / (2 * TILE_M);
+    const uint32_t max_pairs = (uint32_t)ix.sm_count / 2;
+    const unsigned pairs = ntiles < max_pairs ? ntiles : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PKV_CUDA(cudaLaunchKernelEx(&cfg, kernel, mrows, mq128, a, pend, fsn, q0, kchunks, stages));
+    return PKV_OK;
+}
+
+template <int KIND, int METRIC>
 int launch_metric(const Index &ix, const ScanArgs &a, const PendDev &pend, const FloatScan &fsn,
                   const CUtensorMap &mrows, const CUtensorMap &mq128, const CUtensorMap &mq256, int kchunks,
                   SearchStatus *status, cudaStream_t s, int *launches) {
     for (int q0 = 0; q0 < a.nq;) {
         const int left = a.nq - q0;
         *launches += 1;
-        if (left > 128) {
+        if (left > 128 && ix.opt.tc_cta2 && (ix.sm_count % 2) == 0) {
+            PKV_TRY((launch_pair<KIND, METRIC>(ix, a, pend, fsn, mrows, mq128, q0, kchunks, s)));
+            q0 += 256;
+        } else if (left > 128) {
             PKV_TRY((launch_one<KIND, 256, METRIC>(ix, a, pend, fsn, mrows, mq256, q0, kchunks, s)));
             q0 += 256;
         } else {

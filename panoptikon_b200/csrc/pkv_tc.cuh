@@ -180,6 +180,14 @@ __device__ __forceinline__ void mma_tf32_cta2(uint32_t d_tmem, uint64_t a_desc, 
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void mma_f16_cta2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on the mbarrier at this smem offset in BOTH CTAs of the pair once prior MMAs are done
 __device__ __forceinline__ void mma_commit_cta2(uint64_t *bar) {
     asm volatile(

@@ -80,7 +80,7 @@ __global__ void reset_state_kernel(uint32_t *cnt, uint64_t *thr_key, float *thr_
         st->max_raw_cnt = 0;
         st->any_overflow = 0;
         st->min_filled = 0xFFFFFFFFu;
-        st->pad = 0;
+        st->sticky_overflow = 0;
     }
 }
 
@@ -88,7 +88,6 @@ __global__ void reset_status_kernel(SearchStatus *st) {
     st->max_raw_cnt = 0;
     st->any_overflow = 0;
     st->min_filled = 0xFFFFFFFFu;
-    st->pad = 0;
 }
 
 __device__ __forceinline__ float filter_threshold(FilterSpec fs, float d_k, float b_mag) {
@@ -178,7 +177,10 @@ __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *c
         if (s_kth != KEY_MAX) tf = filter_threshold(fs, unordered_bits((uint32_t)(s_kth >> 32)), q_mag_f[q]);
         thr_f[q] = tf;
         atomicMax(&status->max_raw_cnt, raw);
-        if (raw > cap) atomicOr(&status->any_overflow, 1u);
+        if (raw > cap) {
+            atomicOr(&status->any_overflow, 1u);
+            atomicOr(&status->sticky_overflow, 1u);
+        }
         atomicMin(&status->min_filled, m);
     }
 }

@@ -122,3 +122,17 @@ def test_shadow_survives_incremental_appends_with_growing_range():
         x = np.concatenate([x1, x2])
         for metric in METRICS:
             assert_close_topk(ix.search(q, 10, metric), orc.topk(x, q, metric, 10, threads=4), x, q, metric)
+
+
+@pytest.mark.parametrize("shadow", [1, 0])
+def test_tc_float_cta_pair_matches_single_cta(shadow):
+    x, q = orc.synthetic(70007, 512, 261), orc.synthetic(256, 512, 262)
+    with _index(x) as ix:
+        ix.set_option("use_shadow", shadow)
+        for metric in METRICS:
+            pair = ix.search(q, 50, metric)
+            ix.set_option("tc_cta2", 0)
+            single = ix.search(q, 50, metric)
+            ix.set_option("tc_cta2", 1)
+            assert np.array_equal(pair[0], single[0]) and np.array_equal(pair[1].view(np.uint32), single[1].view(np.uint32))
+            assert_close_topk(pair, orc.topk(x, q, metric, 50, threads=16), x, q, metric)
