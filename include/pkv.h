@@ -160,6 +160,15 @@ int pkv_search(pkv_index *h, const void *queries, int nq, const pkv_search_param
 int pkv_search_device(pkv_index *h, const void *d_queries, int nq, const pkv_search_params *params,
                       int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts, void *stream);
 
+/* Untruncated scoring: the exact distance of every stored row to each of nq queries, i.e. the whole
+ * materialised `dist_{cte}` of builder/filters/exact.rs:106-165 (the reference scores every
+ * candidate and only LIMITs at the very end, docs/vector-index-design.md:84-89).
+ * d_out: [nq][rows] f32 in DEVICE memory, row order = stored order; feed it to
+ * pkv_aggregate_device for the per-item MIN/MAX/AVG of builder/filters/exact.rs:67-80.
+ * Meant for interactive batches (nq <= 1024 per call). */
+int pkv_distances_device(pkv_index *h, const void *d_queries, int nq, int metric, int query_dtype, float *d_out,
+                         void *stream);
+
 /* Merge `parts` per-shard result lists (each nq*k, laid out [part][nq][k], as gathered
  * by one NCCL all-gather) into the global top-k under the same total order.
  * DEVICE buffers. */

@@ -76,6 +76,7 @@ SIGNATURES = {
     "pkv_index_get_info": (C.c_int, [_P, C.POINTER(IndexInfo)]),
     "pkv_search": (C.c_int, [_P, _P, C.c_int, C.POINTER(SearchParams), _P, _P, _P]),
     "pkv_search_device": (C.c_int, [_P, _P, C.c_int, C.POINTER(SearchParams), _P, _P, _P, _P]),
+    "pkv_distances_device": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "pkv_merge_topk_device": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pkv_aggregate_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "pkv_index_counters": (C.c_int, [_P, C.POINTER(Counters)]),

@@ -290,7 +290,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // (candidate work per chunk grows with the growth factor, chunk count shrinks with its log:
     // ~4x measured best on B200 for k=100)
     double growth = (double)(ws.cap - k) / (3.0 * k);
-    if (growth > 4.0) growth = 4.0;
+    if (growth > 4.0 && nq >= 32) growth = 4.0;  // few queries: candidates are cheap, chunks are not
     if (ix.opt.chunk_growth_x100 > 0) growth = ix.opt.chunk_growth_x100 / 100.0;
     if (growth < 0.25) growth = 0.25;
     // Optimistic mode: once every query has a threshold (after the first chunk) the remaining chunks
@@ -791,6 +791,53 @@ int pkv_search_device(pkv_index *h, const void *d_queries, int nq, const pkv_sea
                        d_out_counts, (cudaStream_t)stream);
 }
 
+int pkv_distances_device(pkv_index *h, const void *d_queries, int nq, int metric, int query_dtype, float *d_out,
+                         void *stream) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    PKV_TRY(use_device(ix.device));
+    std::shared_lock<std::shared_mutex> lock(ix.mu);
+    pkv_search_params p;
+    memset(&p, 0, sizeof(p));
+    p.metric = metric;
+    p.k = 1;
+    p.query_dtype = query_dtype;
+    int dummy = 0;
+    PKV_TRY(check_search_args(&ix, d_queries, nq, &p, d_out, d_out, &dummy));
+    if (nq == 0 || ix.sealed_rows == 0) return PKV_OK;
+    if (nq > SUB_BATCH) return fail(PKV_ERR_INVALID, "pkv_distances_device takes at most %d queries per call", SUB_BATCH);
+    Workspace *ws = nullptr;
+    PKV_TRY(make_workspace(ix, nq, 1, 0, &ws));
+    struct Guard {
+        Index &ix;
+        Workspace *ws;
+        ~Guard() { release_workspace(ix, ws); }
+    } guard{ix, ws};
+    cudaStream_t s = stream ? (cudaStream_t)stream : ws->stream;
+    PKV_TRY(launch_prep_queries(ix, *ws, d_queries, nq, query_dtype, s));
+    ScanArgs a{};
+    a.data = ix.d_data;
+    a.pitch_bytes = ix.pitch;
+    a.row_begin = 0;
+    a.row_end = (uint32_t)ix.sealed_rows;
+    a.dim_pad = ix.dim_pad;
+    a.dim = ix.dim;
+    a.queries = ws->d_q;
+    a.q_mag_f = ws->d_q_mag_f;
+    a.q_mag_i = ws->d_q_mag_i;
+    a.row_mag_i = ix.d_mag_i;
+    a.row_mag_f = ix.d_mag_f;
+    a.nq = nq;
+    a.metric = metric;
+    a.dense_out = d_out;
+    a.dense_stride = ix.sealed_rows;
+    int n = 0;
+    PKV_TRY(launch_scan_simt(ix, a, s, &n));
+    ix.n_launches += n + 1;
+    PKV_CUDA(cudaStreamSynchronize(s));
+    return PKV_OK;
+}
+
 int pkv_merge_topk_device(int device, const int64_t *d_ids, const float *d_dist, int parts, int nq, int k,
                           int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts, void *stream) {
     PKV_TRY(use_device(device));
@@ -843,6 +890,7 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "simt_bootstrap")) ix.opt.simt_bootstrap = (int)value;
     else if (!strcmp(name, "optimistic")) ix.opt.optimistic = (int)value;
     else if (!strcmp(name, "tc_min_queries_f32")) ix.opt.tc_min_queries_f32 = (int)value;
+    else if (!strcmp(name, "tc_min_queries_img")) ix.opt.tc_min_queries_img = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;
 }

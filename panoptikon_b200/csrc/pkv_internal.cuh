@@ -126,6 +126,8 @@ struct ScanArgs {
     int nq;
     int metric;
     TopkDev topk;
+    float *dense_out;      // non-NULL: write the exact distance of EVERY (query,row) pair here, push nothing
+    int64_t dense_stride;  // elements between consecutive queries in dense_out
 };
 
 struct SearchStatus {  // device -> pinned host after every chunk
@@ -173,13 +175,14 @@ struct Options {
     int64_t first_chunk_rows = 0;    // 0 = auto
     int64_t chunk_growth_x100 = 0;   // 0 = auto
     int time_kernels = 1;
-    int tc_min_queries_f32 = 17;     // f32: the FFMA kernel is HBM-bound up to ~16 queries
+    int tc_min_queries_img = 1;      // f32 with fp16 image: tensor-core filter from the first query
+    int tc_min_queries_f32 = 9;     // f32: the FFMA kernel is HBM-bound up to ~16 queries
     int optimistic = 1;              // enqueue all chunks after the first without host syncs; verify at the end
     int simt_bootstrap = 1;          // threshold-less first chunk runs on the CUDA-core kernel
     int use_shadow = 1;              // f32 index: keep a scaled fp16 image for the tensor-core filter
     int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA
     int tc_cta2 = 1;                 // use the 2-CTA (cta_group::2) kernels when the batch is large enough
-    int tc_min_queries = 9;          // below this the CUDA-core kernels are HBM-bound anyway
+    int tc_min_queries = 1;          // int8: the TMA/tcgen05 kernel streams at ~95% of HBM peak even for one query
 };
 
 struct Index {

@@ -125,6 +125,17 @@ __global__ void __launch_bounds__(THREADS) scan_f32_simt_kernel(const ScanArgs a
                 const int q = g * QB + b;
                 if (!owner || row >= a.row_end || q >= a.nq) continue;
                 const float v = acc[t];
+                if (a.dense_out) {  // full scoring: the reference's untruncated dist CTE
+                    float d;
+                    if (METRIC == PKV_COSINE)
+                        d = cosine_key((double)v, (double)am, (double)__ldg(a.q_mag_f + q));
+                    else if (METRIC == PKV_L2)
+                        d = l2_key_from_sum(v);
+                    else
+                        d = 0.0f - v;
+                    a.dense_out[(size_t)q * a.dense_stride + row] = d;
+                    continue;
+                }
                 const float tf = __ldg(a.topk.thr_f + q);
                 const uint32_t lrow = row;  // local row number inside this index
                 if (METRIC == PKV_COSINE) {
@@ -220,9 +231,15 @@ __global__ void __launch_bounds__(THREADS) scan_i8_simt_kernel(const ScanArgs a)
                 const int q = g * QB + b;
                 if (!owner || row >= a.row_end || q >= a.nq) continue;
                 const int dot = acc[t];
-                const float tf = __ldg(a.topk.thr_f + q);
                 const int am = __ldg(a.row_mag_i + row);
                 const int bm = __ldg(a.q_mag_i + q);
+                if (a.dense_out) {
+                    const int8_t *rowp = (const int8_t *)(base + (size_t)row * (size_t)a.pitch_bytes);
+                    const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
+                    a.dense_out[(size_t)q * a.dense_stride + row] = i8_key(a.metric, dot, am, bm, a.dim, rowp, qp) + 0.0f;
+                    continue;
+                }
+                const float tf = __ldg(a.topk.thr_f + q);
                 float f;
                 if (a.metric == PKV_COSINE)
                     f = -(float)dot * rsqrtf((float)am);
@@ -343,6 +360,17 @@ __global__ void __launch_bounds__(THREADS) scan_f16_simt_kernel(const ScanArgs a
                 const int q = g * QB + b;
                 if (!owner || row >= a.row_end || q >= a.nq) continue;
                 const float v = acc[t];
+                if (a.dense_out) {
+                    float d;
+                    if (METRIC == PKV_COSINE)
+                        d = cosine_key((double)v, (double)am, (double)__ldg(a.q_mag_f + q));
+                    else if (METRIC == PKV_L2)
+                        d = l2_key_from_sum(v);
+                    else
+                        d = 0.0f - v;
+                    a.dense_out[(size_t)q * a.dense_stride + row] = d;
+                    continue;
+                }
                 const float tf = __ldg(a.topk.thr_f + q);
                 if (METRIC == PKV_COSINE) {
                     const float f = -v * rsqrtf(am);

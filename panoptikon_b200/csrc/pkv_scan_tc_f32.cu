@@ -671,7 +671,12 @@ static constexpr float F16_EXACT_EPS = 2.0e-4f;
 
 bool scan_tc_f32_supported(const Index &ix, int nq) {
     if (ix.opt.force_simt) return false;
-    if (ix.dtype == PKV_F32 || ix.dtype == PKV_F16) return nq >= ix.opt.tc_min_queries_f32;
+    // with the fp16 image the tensor-core kernel reads half the bytes of the FFMA kernel, so it
+    // wins from the very first query; the tf32 path reads the f32 rows and only pays off once the
+    // FFMA kernel would need a second pass over the corpus
+    if (ix.dtype == PKV_F32) return (ix.d_shadow && ix.opt.use_shadow) ? nq >= ix.opt.tc_min_queries_img
+                                                                       : nq >= ix.opt.tc_min_queries_f32;
+    if (ix.dtype == PKV_F16) return nq >= ix.opt.tc_min_queries_f32;
     return false;
 }
 

@@ -140,6 +140,20 @@ class VectorIndex:
                                    _np_ptr(counts)))
         return ids, dist, counts
 
+    def distances(self, queries, metric: int = N.COSINE):
+        """Exact distance of EVERY stored row to each query (torch CUDA queries -> [nq, rows] f32 CUDA
+        tensor): the reference's untruncated scoring, input of the per-item aggregation."""
+        import torch
+
+        assert queries.is_cuda and queries.is_contiguous() and queries.dim() == 2
+        if queries.shape[1] != self.dim:
+            raise N.PkvError(N.ERR_DIM_MISMATCH, f"query dimension {queries.shape[1]} != index dimension {self.dim}")
+        out = torch.empty((queries.shape[0], self.rows), dtype=torch.float32, device=queries.device)
+        stream = torch.cuda.current_stream(queries.device).cuda_stream
+        N.check(N.lib().pkv_distances_device(self._h, C.c_void_p(queries.data_ptr()), queries.shape[0], metric,
+                                             _torch_code(queries), C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        return out
+
     def _search_device(self, queries, k, metric, bitmap, bitmap_stride_words, out, stream):
         import torch
 

@@ -109,3 +109,32 @@ def test_aggregate_matches_oracle():
         assert np.allclose(got, want, rtol=1e-12, atol=0, equal_nan=True)
     got = pk.aggregate(td, ti, items + 5, pk.AGG_AVG, weights=tw).cpu().numpy()
     assert np.allclose(got, orc.aggregate(d, item, items + 5, orc.AGG_AVG, weights=w), rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "i8"])
+def test_untruncated_scoring_and_item_aggregation(dtype):
+    """The reference scores EVERY candidate row and aggregates per file (MIN/MAX/AVG,
+    builder/filters/exact.rs:67-80) before any LIMIT: pkv_distances_device + pkv_aggregate_device."""
+    import torch
+
+    n, d, items = 30011, 128, 4000
+    x, q, scale, xc, qc = int8_space(n, d, 97, 3)
+    data, queries, code = (x, q, pk.F32) if dtype == "f32" else (xc, qc, pk.I8)
+    rng = np.random.default_rng(5)
+    item = rng.integers(0, items, n).astype(np.int64)      # several embeddings per item (video frames, text chunks)
+    with pk.VectorIndex(d, code) as ix:
+        ix.append(data); ix.seal()
+        for metric in (pk.COSINE, pk.L2):
+            dist = ix.distances(torch.from_numpy(queries).cuda(), metric)
+            assert dist.shape == (3, n)
+            for qi in range(3):
+                want = orc.distances(data, queries[qi], metric)
+                got = dist[qi].cpu().numpy()
+                if dtype == "i8":
+                    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+                else:
+                    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+                for agg in (pk.AGG_MIN, pk.AGG_AVG, pk.AGG_MAX):
+                    g = pk.aggregate(dist[qi].contiguous(), torch.from_numpy(item).cuda(), items, agg).cpu().numpy()
+                    w = orc.aggregate(want, item, items, agg)
+                    assert np.allclose(g, w, rtol=1e-5 if dtype == "f32" else 1e-12, atol=1e-7, equal_nan=True)

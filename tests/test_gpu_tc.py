@@ -21,7 +21,7 @@ def _index(xc, scale=None):
 
 
 @pytest.mark.parametrize("metric", METRICS)
-@pytest.mark.parametrize("nq", [9, 128, 130, 300, 513])
+@pytest.mark.parametrize("nq", [1, 9, 128, 130, 300, 513])
 def test_tc_int8_bit_exact(metric, nq):
     x, q, scale, xc, qc = int8_space(70001, 768, 101, nq)
     with _index(xc, scale) as ix:
@@ -29,7 +29,7 @@ def test_tc_int8_bit_exact(metric, nq):
         assert ix.counters().last_scan_kind == 3, "tensor-core kernel did not run"
         ix.set_option("force_simt", 1)
         simt = ix.search(qc, 100, metric)
-        assert ix.counters().last_scan_kind == 2
+        assert ix.counters().last_scan_kind == 2, "CUDA-core kernel did not run"
     want = orc.topk(xc, qc, metric, 100, threads=16)
     assert_exact(got, want)
     assert_exact(simt, want)
