@@ -169,6 +169,47 @@ int pkv_search_device(pkv_index *h, const void *d_queries, int nq, const pkv_sea
 int pkv_distances_device(pkv_index *h, const void *d_queries, int nq, int metric, int query_dtype, float *d_out,
                          void *stream);
 
+/* The grouped vector operator: score EVERY stored row against nq query vectors, aggregate per group,
+ * rank the groups — what the filter compilers render as
+ *   SELECT ..., row_number() OVER (ORDER BY AGG(d) ASC) AS order_rank FROM dist_{cte} GROUP BY file_id
+ * (builder/filters/exact.rs:67-80,106-165; builder.rs:757-771).  nq = 1 for image_embeddings /
+ * text_embeddings; nq = the target item's own vectors for similar_to, whose AGG runs over every
+ * (target vector, candidate vector) pair and whose target rows are excluded by group -1
+ * (pql/builder/filters/item_similarity.rs:432-581).
+ *   d_group_of_row : per stored row, the dense group index (file / item, or text data row), or -1
+ *                    when the row is not a candidate (context CTE, the target itself)
+ *   d_weights      : NULL, or per-row w = pow(coalesce(conf,1),wc)*pow(coalesce(lang_conf,1),wl)
+ *                    (exact.rs:37-60) => SUM(d*w)/SUM(w) instead of `aggregation`
+ *   offset / limit : pagination of the ranked list (builder.rs:578-582); offset+limit <= 2048
+ * Output (DEVICE): out_groups[limit] (-1 padded), out_agg[limit] (the aggregate, NaN = SQL NULL;
+ * order_rank of entry i is offset+i+1), *out_count.  Groups without any candidate row are absent;
+ * NULL aggregates rank last; ties by ascending group index. */
+typedef struct {
+    int32_t metric;       /* pkv_metric */
+    int32_t aggregation;  /* pkv_distance_aggregation */
+    int32_t query_dtype;  /* as pkv_search_params */
+    int32_t offset;
+    int32_t limit;
+    int32_t reserved;
+    const int64_t *d_group_of_row;
+    int64_t n_groups;
+    const float *d_weights;
+} pkv_rank_params;
+int pkv_rank_groups_device(pkv_index *h, const void *d_queries, int nq, const pkv_rank_params *params,
+                           int64_t *d_out_groups, double *d_out_agg, int32_t *d_out_count, void *stream);
+/* Copies stored rows (by position) into d_out[n][dim] in the index dtype: similar_to reads the target's
+ * own stored vectors as its queries (item_similarity.rs:352-426). */
+int pkv_index_get_rows_device(pkv_index *h, const int64_t *d_rows, int n, void *d_out, void *stream);
+
+/* Rank fusion of several filters' ranked lists over the same group ids (HOST, lists are <= LIMIT long):
+ * mode 0: RRF, score = SUM_i weight_i * 1.0 / (k_i + coalesce(rank_i, 9223372036854775805)), best = largest
+ *         (build_coalesced_expr, builder.rs:1284-1302);
+ * mode 1 / 2: min / max over the filters of coalesce(rank_i, very large / very small) (builder.rs:1304-1317).
+ * Writes the union of groups ordered best first (ties by group id). */
+int pkv_fuse_ranks(int mode, int n_lists, const int64_t *const *groups, const int64_t *const *ranks, const int32_t *lens,
+                   const double *weights, const int32_t *ks, int64_t *out_groups, double *out_scores, int32_t cap,
+                   int32_t *out_count);
+
 /* Merge `parts` per-shard result lists (each nq*k, laid out [part][nq][k], as gathered
  * by one NCCL all-gather) into the global top-k under the same total order.
  * DEVICE buffers. */

@@ -48,6 +48,14 @@ class Counters(C.Structure):
     ]
 
 
+class RankParams(C.Structure):
+    _fields_ = [
+        ("metric", C.c_int32), ("aggregation", C.c_int32), ("query_dtype", C.c_int32), ("offset", C.c_int32),
+        ("limit", C.c_int32), ("reserved", C.c_int32), ("d_group_of_row", C.c_void_p), ("n_groups", C.c_int64),
+        ("d_weights", C.c_void_p),
+    ]
+
+
 class ReadyPair(C.Structure):
     _fields_ = [("profile_id", C.c_int64), ("scale", C.c_float), ("dim", C.c_int64)]
 
@@ -77,6 +85,9 @@ SIGNATURES = {
     "pkv_search": (C.c_int, [_P, _P, C.c_int, C.POINTER(SearchParams), _P, _P, _P]),
     "pkv_search_device": (C.c_int, [_P, _P, C.c_int, C.POINTER(SearchParams), _P, _P, _P, _P]),
     "pkv_distances_device": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "pkv_rank_groups_device": (C.c_int, [_P, _P, C.c_int, C.POINTER(RankParams), _P, _P, _P, _P]),
+    "pkv_index_get_rows_device": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "pkv_fuse_ranks": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "pkv_merge_topk_device": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pkv_aggregate_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "pkv_index_counters": (C.c_int, [_P, C.POINTER(Counters)]),

@@ -100,7 +100,7 @@ static int make_workspace(Index &ix, int nq, int k, size_t out_rows, Workspace *
         }
     }
     const int cap = candidate_capacity(ix, k);
-    int nq_cap = 16;
+    int nq_cap = 128;  // >= one query tile: TMA boxes over the query buffers never run out of bounds
     const int want = nq < SUB_BATCH ? nq : SUB_BATCH;
     while (nq_cap < want) nq_cap <<= 1;
     if (ws && (ws->nq_cap < nq_cap || ws->cap != cap || ws->dim_pad != ix.dim_pad || ws->out_cap < out_rows)) {
@@ -835,6 +835,46 @@ int pkv_distances_device(pkv_index *h, const void *d_queries, int nq, int metric
     PKV_TRY(launch_scan_simt(ix, a, s, &n));
     ix.n_launches += n + 1;
     PKV_CUDA(cudaStreamSynchronize(s));
+    return PKV_OK;
+}
+
+int pkv_rank_groups_device(pkv_index *h, const void *d_queries, int nq, const pkv_rank_params *p, int64_t *d_out_groups,
+                           double *d_out_agg, int32_t *d_out_count, void *stream) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    if (!p) return fail(PKV_ERR_INVALID, "rank params are NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    PKV_TRY(use_device(ix.device));
+    if (nq < 1) return fail(PKV_ERR_INVALID, "nq must be >= 1");
+    if (p->limit < 1 || p->offset < 0 || p->offset + p->limit > 2048)
+        return fail(PKV_ERR_INVALID, "need limit >= 1, offset >= 0 and offset + limit <= 2048");
+    if (p->aggregation < PKV_AGG_MIN || p->aggregation > PKV_AGG_AVG) return fail(PKV_ERR_INVALID, "unknown aggregation");
+    if (p->n_groups < 0 || p->n_groups >= 0xFFFFFFFFll) return fail(PKV_ERR_INVALID, "n_groups out of range");
+    if (!p->d_group_of_row || !d_out_groups || !d_out_agg || !d_out_count) return fail(PKV_ERR_INVALID, "NULL buffer");
+    const int64_t rows = ix.sealed_rows;
+    if ((double)rows * nq > 4.0e9)
+        return fail(PKV_ERR_UNSUPPORTED, "%d query vectors x %lld rows exceeds the dense scoring buffer", nq, (long long)rows);
+    cudaStream_t s = (cudaStream_t)stream;
+    float *d_dist = nullptr;
+    PKV_CUDA(cudaMallocAsync((void **)&d_dist, sizeof(float) * (size_t)(rows > 0 ? rows : 1) * nq, s));
+    if (!s) PKV_CUDA(cudaStreamSynchronize(s));  // the scoring pass below runs on a workspace stream
+    int st = rows > 0 ? pkv_distances_device(h, d_queries, nq, p->metric, p->query_dtype, d_dist, stream) : PKV_OK;
+    if (st == PKV_OK)
+        st = rank_groups(d_dist, rows, nq, p->d_group_of_row, p->d_weights, p->n_groups, p->aggregation, p->offset,
+                         p->limit, d_out_groups, d_out_agg, d_out_count, s);
+    cudaFreeAsync(d_dist, s);
+    if (st != PKV_OK) return st;
+    PKV_CUDA(cudaStreamSynchronize(s));
+    return PKV_OK;
+}
+
+int pkv_index_get_rows_device(pkv_index *h, const int64_t *d_rows, int n, void *d_out, void *stream) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    PKV_TRY(use_device(ix.device));
+    if (n < 0 || (n > 0 && (!d_rows || !d_out))) return fail(PKV_ERR_INVALID, "bad arguments");
+    std::shared_lock<std::shared_mutex> lock(ix.mu);
+    PKV_TRY(launch_gather_rows(ix, d_rows, n, d_out, (cudaStream_t)stream));
+    PKV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return PKV_OK;
 }
 

@@ -228,6 +228,11 @@ int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaSt
 int scan_tc_f32_kind(const Index &ix);
 int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);
 
+// pkv_operator.cu
+int rank_groups(const float *d_dist, int64_t rows, int nq, const int64_t *d_group_of_row, const float *d_weights,
+                int64_t n_groups, int agg, int offset, int limit, int64_t *d_out_groups, double *d_out_agg,
+                int32_t *d_out_count, cudaStream_t s);
+int launch_gather_rows(const Index &ix, const int64_t *d_rows, int n, void *d_out, cudaStream_t s);
 // pkv_topk.cu
 int launch_reset_status(Workspace &ws, cudaStream_t s);
 int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);

@@ -13,6 +13,8 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <unordered_map>
 
 #include "../../include/pkv.h"
 
@@ -229,3 +231,56 @@ int pkv_space_search(pkv_space *s, const float *queries, int nq, int query_dim, 
 }
 
 }  // extern "C"
+
+// ---- rank fusion (builder.rs:1284-1317) -----------------------------------------------------
+extern "C" int pkv_fuse_ranks(int mode, int n_lists, const int64_t *const *groups, const int64_t *const *ranks,
+                              const int32_t *lens, const double *weights, const int32_t *ks, int64_t *out_groups,
+                              double *out_scores, int32_t cap, int32_t *out_count) {
+    if (mode < 0 || mode > 2 || n_lists < 1 || !groups || !ranks || !lens || !out_groups || !out_scores || !out_count)
+        return fail(PKV_ERR_INVALID, "bad fuse arguments");
+    if (mode == 0 && (!weights || !ks)) return fail(PKV_ERR_INVALID, "RRF needs weights and k per list");
+    const double VERY_LARGE = 9223372036854775805.0, VERY_SMALL = -9223372036854775805.0;
+    std::unordered_map<int64_t, std::vector<int64_t>> seen;  // group -> rank per list (INT64_MIN = missing)
+    const int64_t MISSING = INT64_MIN;
+    for (int l = 0; l < n_lists; ++l) {
+        if (lens[l] < 0 || (lens[l] > 0 && (!groups[l] || !ranks[l]))) return fail(PKV_ERR_INVALID, "bad list %d", l);
+        for (int i = 0; i < lens[l]; ++i) {
+            auto &v = seen[groups[l][i]];
+            if (v.empty()) v.assign((size_t)n_lists, MISSING);
+            v[(size_t)l] = ranks[l][i];
+        }
+    }
+    struct Row {
+        int64_t g;
+        double score;
+    };
+    std::vector<Row> rows;
+    rows.reserve(seen.size());
+    for (auto &kv : seen) {
+        double score = mode == 1 ? VERY_LARGE : (mode == 2 ? VERY_SMALL : 0.0);
+        for (int l = 0; l < n_lists; ++l) {
+            const int64_t r = kv.second[(size_t)l];
+            if (mode == 0) {
+                const double rank = r == MISSING ? VERY_LARGE : (double)r;
+                score += (1.0 / ((double)ks[l] + rank)) * weights[l];  // `1.0 / (k + rank) * weight`
+            } else if (mode == 1) {
+                score = std::min(score, r == MISSING ? VERY_LARGE : (double)r);
+            } else {
+                score = std::max(score, r == MISSING ? VERY_SMALL : (double)r);
+            }
+        }
+        rows.push_back(Row{kv.first, score});
+    }
+    const bool desc = mode != 1;  // RRF score and max-rank order descending, min-rank ascending
+    std::sort(rows.begin(), rows.end(), [desc](const Row &a, const Row &b) {
+        if (a.score != b.score) return desc ? a.score > b.score : a.score < b.score;
+        return a.g < b.g;
+    });
+    const int32_t n = (int32_t)std::min<size_t>(rows.size(), (size_t)(cap > 0 ? cap : 0));
+    for (int32_t i = 0; i < n; ++i) {
+        out_groups[i] = rows[(size_t)i].g;
+        out_scores[i] = rows[(size_t)i].score;
+    }
+    *out_count = n;
+    return PKV_OK;
+}

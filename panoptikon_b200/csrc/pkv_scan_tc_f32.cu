@@ -716,11 +716,17 @@ int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaSt
     fsn.q_scale = nullptr;
     fsn.tiny_mag = 0.f;
     CUtensorMap mrows, mq128, mq256;
+    // Query maps span whole 128-row tiles of the (larger) workspace buffer: an out-of-bounds TMA box is
+    // zero-filled row by row and measurably slower; rows past nq hold stale queries whose accumulator
+    // columns the epilogue ignores.
+    uint64_t qrows = ((uint64_t)a.nq + 127) / 128 * 128;
+    if (qrows > (uint64_t)ws.nq_cap) qrows = (uint64_t)ws.nq_cap;
+    if (qrows < (uint64_t)a.nq) qrows = (uint64_t)a.nq;
     const bool shadow = use_shadow(ix);
     if (ix.dtype == PKV_F32 && !shadow) {
         PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.pitch, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
-        PKV_TRY(make_tmap_bytes(&mq128, a.queries, (uint64_t)ix.pitch, (uint64_t)a.nq, (uint64_t)ix.pitch, 128));
-        PKV_TRY(make_tmap_bytes(&mq256, a.queries, (uint64_t)ix.pitch, (uint64_t)a.nq, (uint64_t)ix.pitch, 256));
+        PKV_TRY(make_tmap_bytes(&mq128, a.queries, (uint64_t)ix.pitch, qrows, (uint64_t)ix.pitch, 128));
+        PKV_TRY(make_tmap_bytes(&mq256, a.queries, (uint64_t)ix.pitch, qrows, (uint64_t)ix.pitch, 256));
         return launch_kind<KIND_TF32>(ix, a, pend, fsn, mrows, mq128, mq256, (int)(ix.pitch / CHUNK_BYTES), ws.d_status, s,
                                       launches);
     }
@@ -739,8 +745,8 @@ int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaSt
         fsn.tiny_mag = lim * lim;
     }
     PKV_TRY(make_tmap_bytes(&mrows, img, pitch_h, (uint64_t)ix.sealed_rows, pitch_h, TILE_M));
-    PKV_TRY(make_tmap_bytes(&mq128, ws.d_q16, pitch_h, (uint64_t)a.nq, pitch_h, 128));
-    PKV_TRY(make_tmap_bytes(&mq256, ws.d_q16, pitch_h, (uint64_t)a.nq, pitch_h, 256));
+    PKV_TRY(make_tmap_bytes(&mq128, ws.d_q16, pitch_h, qrows, pitch_h, 128));
+    PKV_TRY(make_tmap_bytes(&mq256, ws.d_q16, pitch_h, qrows, pitch_h, 256));
     return launch_kind<KIND_F16>(ix, a, pend, fsn, mrows, mq128, mq256, (int)(pitch_h / CHUNK_BYTES), ws.d_status, s,
                                  launches);
 }

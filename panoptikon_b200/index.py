@@ -154,6 +154,38 @@ class VectorIndex:
                                              _torch_code(queries), C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
         return out
 
+    def get_rows(self, rows):
+        """Stored vectors at the given positions (torch int64 CUDA tensor) -> [n, dim] CUDA tensor."""
+        import torch
+
+        dt = {N.F32: torch.float32, N.I8: torch.int8, N.F16: torch.float16}[self.dtype]
+        out = torch.empty((rows.numel(), self.dim), dtype=dt, device=rows.device)
+        stream = torch.cuda.current_stream(rows.device).cuda_stream
+        N.check(N.lib().pkv_index_get_rows_device(self._h, C.c_void_p(rows.data_ptr()), rows.numel(),
+                                                  C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        return out
+
+    def rank_groups(self, queries, group_of_row, n_groups: int, aggregation: int = N.AGG_MIN, metric: int = N.COSINE,
+                    weights=None, offset: int = 0, limit: int = 320):
+        """The grouped vector operator (score every row, aggregate per group, rank): torch CUDA tensors in,
+        (groups[limit] int64, aggregates[limit] f64, count) CUDA tensors out; order_rank of entry i is
+        offset + i + 1."""
+        import torch
+
+        assert queries.is_cuda and queries.is_contiguous() and queries.dim() == 2
+        assert group_of_row.is_cuda and group_of_row.dtype == torch.int64 and group_of_row.numel() == self.rows
+        p = N.RankParams(metric=metric, aggregation=aggregation, query_dtype=_torch_code(queries), offset=offset,
+                         limit=limit, d_group_of_row=group_of_row.data_ptr(), n_groups=n_groups,
+                         d_weights=None if weights is None else weights.data_ptr())
+        groups = torch.empty(limit, dtype=torch.int64, device=queries.device)
+        agg = torch.empty(limit, dtype=torch.float64, device=queries.device)
+        count = torch.empty(1, dtype=torch.int32, device=queries.device)
+        stream = torch.cuda.current_stream(queries.device).cuda_stream
+        N.check(N.lib().pkv_rank_groups_device(self._h, C.c_void_p(queries.data_ptr()), queries.shape[0], C.byref(p),
+                                               C.c_void_p(groups.data_ptr()), C.c_void_p(agg.data_ptr()),
+                                               C.c_void_p(count.data_ptr()), C.c_void_p(stream)))
+        return groups, agg, int(count.item())
+
     def _search_device(self, queries, k, metric, bitmap, bitmap_stride_words, out, stream):
         import torch
 
@@ -252,3 +284,22 @@ def aggregate(dist, item_of_row, n_items: int, agg: int, weights=None, device: i
                                          None if weights is None else C.c_void_p(weights.data_ptr()),
                                          dist.numel(), n_items, agg, C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
     return out
+
+
+def fuse_ranks(lists, mode: str = "rrf", weights=None, ks=None, cap: int = 4096):
+    """Rank fusion over several filters' (groups, ranks) lists (builder.rs:1284-1317).
+    mode "rrf": sum_i w_i / (k_i + rank_i), best = largest; "min"/"max": coalesced min / max rank."""
+    m = {"rrf": 0, "min": 1, "max": 2}[mode]
+    n = len(lists)
+    g_arr = [np.ascontiguousarray(g, dtype=np.int64) for g, _ in lists]
+    r_arr = [np.ascontiguousarray(r, dtype=np.int64) for _, r in lists]
+    gp = (C.c_void_p * n)(*[a.ctypes.data for a in g_arr])
+    rp = (C.c_void_p * n)(*[a.ctypes.data for a in r_arr])
+    lens = (C.c_int32 * n)(*[len(a) for a in g_arr])
+    w = (C.c_double * n)(*(weights if weights is not None else [1.0] * n))
+    k = (C.c_int32 * n)(*(ks if ks is not None else [60] * n))
+    out_g = np.empty(cap, np.int64)
+    out_s = np.empty(cap, np.float64)
+    cnt = C.c_int32()
+    N.check(N.lib().pkv_fuse_ranks(m, n, gp, rp, lens, w, k, _np_ptr(out_g), _np_ptr(out_s), cap, C.byref(cnt)))
+    return out_g[: cnt.value], out_s[: cnt.value]

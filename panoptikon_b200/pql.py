@@ -117,3 +117,20 @@ class Space:
             raise PqlError(N.last_error())
         N.check(st)
         return ids, dist, counts, used.value
+
+
+def similar_to(index: VectorIndex, item_of_row, n_items: int, target_item: int, distance_function: int,
+               distance_aggregation: int = N.AGG_AVG, weights=None, offset: int = 0, limit: int = 320):
+    """`similar_to` (pql/builder/filters/item_similarity.rs:432-581): the target item's stored vectors are the
+    queries, every other item's vectors the candidates, the aggregate (AVG by default,
+    item_similarity.rs:127-130) runs over all (target vector, candidate vector) pairs, the target itself
+    is excluded.  item_of_row: torch int64 CUDA tensor, dense item index per stored row.
+    Returns (items, aggregates, count)."""
+    import torch
+
+    target_rows = torch.nonzero(item_of_row == target_item).flatten()
+    if target_rows.numel() == 0:
+        raise PqlError(f"item {target_item} has no embeddings for this model")
+    queries = index.get_rows(target_rows.contiguous())
+    groups = torch.where(item_of_row == target_item, torch.full_like(item_of_row, -1), item_of_row).contiguous()
+    return index.rank_groups(queries, groups, n_items, distance_aggregation, distance_function, weights, offset, limit)

@@ -138,3 +138,96 @@ def test_untruncated_scoring_and_item_aggregation(dtype):
                     g = pk.aggregate(dist[qi].contiguous(), torch.from_numpy(item).cuda(), items, agg).cpu().numpy()
                     w = orc.aggregate(want, item, items, agg)
                     assert np.allclose(g, w, rtol=1e-5 if dtype == "f32" else 1e-12, atol=1e-7, equal_nan=True)
+
+
+def _rank_reference(dist_rows, group_of_row, n_groups, agg, weights=None):
+    """NumPy restatement of GROUP BY + ORDER BY AGG(d) ASC NULLS LAST over oracle distances."""
+    nq, n = dist_rows.shape
+    flat_d = dist_rows.reshape(-1)
+    flat_g = np.tile(group_of_row, nq)
+    flat_w = None if weights is None else np.tile(weights, nq)
+    ok = flat_g >= 0
+    a = orc.aggregate(flat_d[ok], flat_g[ok], n_groups, agg, None if flat_w is None else flat_w[ok])
+    present = np.zeros(n_groups, bool)
+    present[flat_g[ok]] = True
+    ids = np.nonzero(present)[0]
+    nan = np.isnan(a[ids])
+    order = ids[np.lexsort((ids, np.where(nan, np.inf, a[ids]), nan))]
+    return order, a
+
+
+@pytest.mark.parametrize("dtype", ["f32", "i8"])
+def test_grouped_operator_rank_matches_sql_semantics(dtype):
+    import torch
+
+    n, d, n_groups = 40009, 96, 6000
+    x, q, scale, xc, qc = int8_space(n, d, 131, 2)
+    data, queries, code = (x, q, pk.F32) if dtype == "f32" else (xc, qc, pk.I8)
+    rng = np.random.default_rng(7)
+    group = rng.integers(0, n_groups - 50, n).astype(np.int64)   # the last 50 groups own no row: absent
+    group[rng.random(n) < 0.2] = -1                               # rows outside the context CTE
+    data = data.copy()
+    data[group == 17] = 0                                         # a group with only zero vectors: NULL cosine
+    w = (rng.random(n) + 0.05).astype(np.float32)
+    with pk.VectorIndex(d, code) as ix:
+        ix.append(data); ix.seal()
+        tg, tw = torch.from_numpy(group).cuda(), torch.from_numpy(w).cuda()
+        for metric in (pk.COSINE, pk.L2):
+            dist = np.stack([orc.distances(data, queries[0], metric)])
+            for agg, weights in ((pk.AGG_MIN, None), (pk.AGG_MAX, None), (pk.AGG_AVG, None), (pk.AGG_AVG, w)):
+                order, a = _rank_reference(dist, group, n_groups, agg, weights)
+                for offset, limit in ((0, 320), (320, 100)):
+                    g, v, cnt = ix.rank_groups(torch.from_numpy(queries[:1]).cuda(), tg, n_groups, agg, metric,
+                                               None if weights is None else tw, offset, limit)
+                    g, v = g.cpu().numpy(), v.cpu().numpy()
+                    want = order[offset:offset + limit]
+                    assert cnt == len(want)
+                    if dtype == "i8" and weights is None and agg != pk.AGG_AVG:
+                        assert list(g[:cnt]) == list(want)          # exact distances: exact order
+                    else:
+                        # float sums differ in the last bits: same aggregates, order equal up to near-ties
+                        assert np.allclose(v[:cnt], a[want], rtol=2e-5, atol=1e-6, equal_nan=True)
+                        assert len(set(g[:cnt]) ^ set(want)) <= 4
+                    assert np.allclose(v[:cnt], a[g[:cnt]], rtol=2e-5, atol=1e-6, equal_nan=True)
+        # the all-NULL group is ranked last (NULLS LAST), absent groups never appear
+        g, v, cnt = ix.rank_groups(torch.from_numpy(queries[:1]).cuda(), tg, n_groups, pk.AGG_MIN, pk.COSINE, None, 0, 2048)
+        assert cnt == 2048 or 17 in g.cpu().numpy()[:cnt]
+
+
+def test_similar_to_matches_reference_fixture_and_oracle():
+    """db/vector_quants.rs:3532-3582 fixture through the operator (AVG over target x candidate pairs,
+    target excluded), f32 and int8 agree; plus a multi-vector target against the NumPy restatement."""
+    import json, os
+    import torch
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["similar_to"]
+    seeded = np.array(g["vectors"], np.float32)
+    space = np.concatenate([seeded, np.tile(np.array(g["filler"], np.float32), (g["total_vectors"] - len(seeded), 1))])
+    scale = pk.scale_from_absmax(pk.blob_absmax(space))
+    codes = pk.quantize_int8(space, scale)
+    n = len(seeded)
+    item = torch.arange(n, dtype=torch.int64).cuda()
+    orders = []
+    for code, data in ((pk.F32, seeded), (pk.I8, codes[:n])):
+        with pk.VectorIndex(8, code) as ix:
+            ix.append(data); ix.seal()
+            items, agg, cnt = pk.similar_to(ix, item, n, g["target_index"], pk.L2)
+            assert cnt == 7
+            orders.append(list(items.cpu().numpy()[:cnt]))
+    assert orders[0] == orders[1] and g["target_index"] not in orders[0]
+
+    # multi-vector items: 3 vectors per item, AVG over all 3 x 3 pairs
+    x = orc.synthetic(3000, 64, 141)
+    it = np.repeat(np.arange(1000), 3).astype(np.int64)
+    with pk.VectorIndex(64, pk.F32) as ix:
+        ix.append(x); ix.seal()
+        for agg in (pk.AGG_AVG, pk.AGG_MIN):
+            items, vals, cnt = pk.similar_to(ix, torch.from_numpy(it).cuda(), 1000, 42, pk.COSINE, agg, limit=50)
+            tq = x[it == 42]
+            dist = np.stack([orc.distances(x, t, orc.COSINE) for t in tq])
+            grp = np.where(it == 42, -1, it)
+            order, a = _rank_reference(dist, grp, 1000, agg)
+            got = items.cpu().numpy()[:cnt]
+            assert cnt == 50 and 42 not in got
+            assert np.allclose(vals.cpu().numpy()[:cnt], a[order[:50]], rtol=2e-5, atol=1e-6)
+            assert len(set(got) ^ set(order[:50])) <= 2

@@ -90,3 +90,27 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert not re.search(r"#include\s+[\"<].*oracle", text), f
+
+
+def test_rank_fusion_matches_the_sql_expression():
+    """build_coalesced_expr (pql/builder.rs:1284-1317): RRF = sum_i 1.0/(k_i + coalesce(rank_i, HUGE)) * w_i;
+    otherwise min / max over the filters of the coalesced ranks."""
+    rng = np.random.default_rng(0)
+    HUGE = 9223372036854775805.0
+    lists, ks, ws = [], [60, 0, 10], [1.0, 0.5, 2.0]
+    for _ in range(3):
+        g = rng.choice(500, size=200, replace=False)
+        lists.append((g, np.arange(1, 201)))
+    groups = sorted(set(np.concatenate([g for g, _ in lists]).tolist()))
+    rank = [{int(g): int(r) for g, r in zip(*l)} for l in lists]
+    want = {g: sum(1.0 / (ks[i] + rank[i].get(g, HUGE)) * ws[i] for i in range(3)) for g in groups}
+    order = sorted(groups, key=lambda g: (-want[g], g))
+    got_g, got_s = pk.fuse_ranks(lists, "rrf", ws, ks)
+    assert list(got_g) == order
+    assert np.allclose(got_s, [want[g] for g in order], rtol=1e-15)
+    mn = {g: min(rank[i].get(g, HUGE) for i in range(3)) for g in groups}
+    got_g, got_s = pk.fuse_ranks(lists, "min")
+    assert list(got_g) == sorted(groups, key=lambda g: (mn[g], g))
+    mx = {g: max(rank[i].get(g, -HUGE) for i in range(3)) for g in groups}
+    got_g, got_s = pk.fuse_ranks(lists, "max")
+    assert list(got_g) == sorted(groups, key=lambda g: (-mx[g], g))
