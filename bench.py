@@ -390,11 +390,18 @@ def main():
     achieved_gbs = alg_bytes / (scan_ms_step * 1e-3) / 1e9 if scan_ms_step > 0 else 0.0
     ops = 2.0 * a.batch * shard_rows * a.dim
     tput = ops / (scan_ms_step * 1e-3) / 1e12 if scan_ms_step > 0 else 0.0
-    tensor_bound = kind in (3, 6) and a.batch >= 512
+    # Which roof binds: passes of <= 128 queries stream the scanned image at HBM speed (ncu: ~85 % DRAM
+    # throughput, tensor pipe ~40 % active); 256-query passes keep the tensor pipe ~77 % active with DRAM
+    # at ~53 % (profiles/r01_ncu_*), i.e. they are tensor/smem-bound.
+    tensor_bound = kind in (3, 4, 6, 7) and a.batch > 128
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)   # burst figure: the timed region is a fraction of a second
+    tensor_peak = 2.0 * bf16_peak if a.dtype == "i8" else (0.5 * bf16_peak if kind == 4 else bf16_peak)
     roofline = {
         "bound": "tensor" if tensor_bound else "hbm",
         "achieved": tput if tensor_bound else achieved_gbs,
-        "peak": None, "unit": "TOP/s" if tensor_bound else "GB/s", "frac": None, "traffic": None,
+        "peak": tensor_peak if tensor_bound else hbm_peak,
+        "unit": ("TOP/s" if a.dtype == "i8" else "TFLOP/s") if tensor_bound else "GB/s",
+        "frac": None, "traffic": None,
         "kernel": {1: "scan_f32_simt", 2: "scan_i8_simt", 3: "scan_i8_tc (tcgen05 kind::i8)",
                    4: "scan_float_tc (tcgen05 kind::tf32 filter on f32 rows + exact rescore)", 5: "scan_f16_simt",
                    6: "scan_float_tc (tcgen05 kind::f16 on f16 rows + exact rescore)",
@@ -404,16 +411,23 @@ def main():
         "f32_equivalent_gbs": (shard_rows * a.dim * 4 / (scan_ms_step * 1e-3) / 1e9) if (kind == 7 and scan_ms_step > 0) else None,
         "launches_per_step": scan_launches, "kernel_ms_per_step": scan_ms_step,
         "algorithmic_bytes_per_step": alg_bytes, "algorithmic_ops_per_step": ops,
-        "achieved_gbs": achieved_gbs, "achieved_tops": tput, "peak_source": peak_src,
+        "achieved_gbs": achieved_gbs, "achieved_tops": tput,
+        "hbm_frac": achieved_gbs / hbm_peak if hbm_peak else None,
+        "tensor_frac": tput / tensor_peak if tensor_peak else None,
+        "peak_source": peak_src + ("; tensor peak = measured cuBLAS bf16 burst" +
+                                   (" x2 (the int8 pipe runs at twice the bf16 rate; nominal 4500)" if a.dtype == "i8" else "")
+                                   if tensor_bound else ""),
     }
-    if tensor_bound:
-        # int8 dense peak is not in MEASURED_PEAKS.json: 2x the measured bf16 figure (the int8 pipe is
-        # 2x bf16 on sm_100), nominal 4500 shown beside it
-        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-        roofline["peak"] = 2.0 * bf16 if a.dtype == "i8" else bf16
-        roofline["peak_nominal"] = 4500.0 if a.dtype == "i8" else 2250.0
-    else:
-        roofline["peak"] = hbm_peak
+    # DRAM traffic: ncu --set full on the main-chunk launches measured dram__bytes_read+write = 1.0005x
+    # (scan_float_tc2, 11.587 GB vs 11.581 GB algorithmic) and 1.0024x (scan_i8_tc) of the bytes of the rows
+    # the launch covers (profiles/r01_ncu_*.txt): no re-reads inside a pass.  A batch wider than one query
+    # tile makes one pass per tile, and every pass streams the image again.
+    sub = min(a.batch, 1024)
+    tiles = (-(-sub // 256) if sub > 128 else 1) if kind in (3, 4, 6, 7) else -(-sub // 8)
+    roofline["passes_per_step"] = tiles * -(-a.batch // 1024)
+    roofline["traffic"] = roofline["passes_per_step"] * alg_bytes * 1.002
+    roofline["traffic_note"] = ("estimated: passes_per_step x algorithmic bytes x 1.002, the ratio ncu measured on the "
+                                "main-chunk launches (profiles/r01_ncu_*.txt)")
     roofline["frac"] = roofline["achieved"] / roofline["peak"] if roofline["peak"] else None
 
     line = {

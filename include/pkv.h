@@ -20,7 +20,8 @@
  *     migrations/index/20260730150000_embedding_quants_rowid.sql:32-48), no header.
  *   - all entry points are re-entrant; searches may run concurrently from many
  *     threads (the reference's read pool is 16 threads: db/connection.rs:235),
- *     append/seal take the index exclusively.
+ *     append/seal take the index exclusively.  Concurrent small pkv_search calls with the
+ *     same metric/k are combined into one pass over the corpus (no added wait when idle).
  *   - there is NO CPU fallback: every compute entry point fails with
  *     PKV_ERR_CUDA when no sm_100 device is usable.
  *
@@ -232,12 +233,15 @@ typedef struct {
     int64_t fallback_queries;   /* queries re-run on the small-chunk schedule after a candidate overflow */
     double last_scan_ms;        /* CUDA-event time of the scan kernels of the last search on this thread */
     double last_total_ms;       /* CUDA-event time of the last search's device work */
-    int32_t last_scan_kind;     /* which scan kernel family ran: 1 simt-f32, 2 simt-i8, 3 tc-i8, 4 tc-tf32, 5 simt-f16, 6 tc-f16 */
+    int32_t last_scan_kind;     /* which scan kernel family ran: 1 simt-f32, 2 simt-i8, 3 tc-i8, 4 tc-tf32, 5 simt-f16,
+                                   6 tc-f16 (f16 rows), 7 tc-f16 on the fp16 image of f32 rows */
     int32_t reserved;
+    int64_t combined_searches;  /* host searches that shared one corpus scan with concurrent callers */
 } pkv_counters;
 int pkv_index_counters(pkv_index *h, pkv_counters *out);
-/* Tuning knobs for tests and the bench: name = "force_simt" (0/1), "candidate_capacity",
- * "first_chunk_rows", "chunk_growth_x100", "time_kernels" (0/1). */
+/* Tuning knobs for tests and the bench: "force_simt", "use_shadow", "tc_cta2", "tc_min_queries",
+ * "tc_min_queries_f32", "tc_min_queries_img", "candidate_capacity", "first_chunk_rows",
+ * "chunk_growth_x100", "optimistic", "simt_bootstrap", "combine", "time_kernels", "tc_prefetch_tiles". */
 int pkv_index_set_option(pkv_index *h, const char *name, int64_t value);
 
 /* -- PQL operator policy: pql/preprocess.rs:314-465, builder/filters/embedding_types.rs --- */

@@ -44,7 +44,7 @@ class Counters(C.Structure):
         ("searches", C.c_int64), ("queries", C.c_int64), ("kernel_launches", C.c_int64),
         ("scan_launches", C.c_int64), ("fallback_queries", C.c_int64),
         ("last_scan_ms", C.c_double), ("last_total_ms", C.c_double),
-        ("last_scan_kind", C.c_int32), ("reserved", C.c_int32),
+        ("last_scan_kind", C.c_int32), ("reserved", C.c_int32), ("combined_searches", C.c_int64),
     ]
 
 

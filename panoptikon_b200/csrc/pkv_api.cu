@@ -451,6 +451,88 @@ static int search_impl(Index &ix, const void *queries, bool host_io, int nq, con
     return PKV_OK;
 }
 
+// ------------------------------------------------------------ combining
+static void run_group(Index &ix, std::vector<PendingSearch *> &group) {
+    if (group.size() == 1) {
+        PendingSearch &g = *group[0];
+        g.status = search_impl(ix, g.queries, true, g.nq, g.params, g.out_ids, g.out_dist, g.out_counts, nullptr);
+        if (g.status != PKV_OK) g.error = g_last_error;
+        return;
+    }
+    const pkv_search_params &p = group[0]->params;
+    const size_t qbytes = (size_t)ix.dim * elem_size(p.query_dtype);
+    int total = 0;
+    for (auto *g : group) total += g->nq;
+    std::vector<uint8_t> q((size_t)total * qbytes);
+    std::vector<int64_t> ids((size_t)total * p.k);
+    std::vector<float> dist((size_t)total * p.k);
+    std::vector<int32_t> cnt((size_t)total);
+    size_t off = 0;
+    for (auto *g : group) {
+        memcpy(q.data() + off * qbytes, g->queries, (size_t)g->nq * qbytes);
+        off += g->nq;
+    }
+    const int st = search_impl(ix, q.data(), true, total, p, ids.data(), dist.data(), cnt.data(), nullptr);
+    off = 0;
+    for (auto *g : group) {
+        g->status = st;
+        if (st != PKV_OK) {
+            g->error = g_last_error;
+        } else {
+            memcpy(g->out_ids, ids.data() + off * p.k, sizeof(int64_t) * (size_t)g->nq * p.k);
+            memcpy(g->out_dist, dist.data() + off * p.k, sizeof(float) * (size_t)g->nq * p.k);
+            memcpy(g->out_counts, cnt.data() + off, sizeof(int32_t) * (size_t)g->nq);
+        }
+        off += g->nq;
+    }
+    ix.n_combined += (int64_t)group.size();
+}
+
+static int combined_search(Index &ix, const void *queries, int nq, const pkv_search_params &p, int64_t *out_ids,
+                           float *out_dist, int32_t *out_counts) {
+    PendingSearch me;
+    me.queries = queries;
+    me.nq = nq;
+    me.params = p;
+    me.out_ids = out_ids;
+    me.out_dist = out_dist;
+    me.out_counts = out_counts;
+    Combiner &c = ix.comb;
+    std::unique_lock<std::mutex> lk(c.mu);
+    c.queue.push_back(&me);
+    while (!me.done) {
+        if (c.busy) {
+            c.cv.wait(lk);
+            continue;
+        }
+        // become the executor: serve the oldest request and everything queued that can share its scan
+        c.busy = true;
+        std::vector<PendingSearch *> group;
+        const pkv_search_params key = c.queue.front()->params;
+        int total = 0;
+        for (auto it = c.queue.begin(); it != c.queue.end();) {
+            PendingSearch *g = *it;
+            const bool same = g->params.metric == key.metric && g->params.k == key.k &&
+                              g->params.query_dtype == key.query_dtype;
+            if (same && total + g->nq <= SUB_BATCH) {
+                group.push_back(g);
+                total += g->nq;
+                it = c.queue.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        lk.unlock();
+        run_group(ix, group);
+        lk.lock();
+        for (auto *g : group) g->done = true;
+        c.busy = false;
+        c.cv.notify_all();
+    }
+    if (me.status != PKV_OK) g_last_error = me.error;
+    return me.status;
+}
+
 // ------------------------------------------------------------ index storage
 static int grow(Index &ix, int64_t need_rows, bool exact = false) {
     if (need_rows <= ix.cap_rows) return PKV_OK;
@@ -779,8 +861,11 @@ int pkv_search(pkv_index *h, const void *queries, int nq, const pkv_search_param
                float *out_dist, int32_t *out_counts) {
     if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
     if (!params) return fail(PKV_ERR_INVALID, "search params are NULL");
-    return search_impl(*reinterpret_cast<Index *>(h), queries, true, nq, *params, out_ids, out_dist, out_counts,
-                       nullptr);
+    Index &ix = *reinterpret_cast<Index *>(h);
+    if (ix.opt.combine && nq > 0 && nq <= 64 && !params->bitmap && queries && out_ids && out_dist && out_counts &&
+        params->k >= 1 && params->k <= PKV_MAX_K)
+        return combined_search(ix, queries, nq, *params, out_ids, out_dist, out_counts);
+    return search_impl(ix, queries, true, nq, *params, out_ids, out_dist, out_counts, nullptr);
 }
 
 int pkv_search_device(pkv_index *h, const void *d_queries, int nq, const pkv_search_params *params, int64_t *d_out_ids,
@@ -908,6 +993,7 @@ int pkv_index_counters(pkv_index *h, pkv_counters *out) {
     out->kernel_launches = ix.n_launches;
     out->scan_launches = ix.n_scan_launches;
     out->fallback_queries = ix.n_fallback;
+    out->combined_searches = ix.n_combined;
     out->last_scan_ms = ix.last_scan_ms;
     out->last_total_ms = ix.last_total_ms;
     out->last_scan_kind = ix.last_scan_kind;
@@ -929,6 +1015,7 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "use_shadow")) ix.opt.use_shadow = (int)value;
     else if (!strcmp(name, "simt_bootstrap")) ix.opt.simt_bootstrap = (int)value;
     else if (!strcmp(name, "optimistic")) ix.opt.optimistic = (int)value;
+    else if (!strcmp(name, "combine")) ix.opt.combine = (int)value;
     else if (!strcmp(name, "tc_min_queries_f32")) ix.opt.tc_min_queries_f32 = (int)value;
     else if (!strcmp(name, "tc_min_queries_img")) ix.opt.tc_min_queries_img = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);

@@ -17,6 +17,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <shared_mutex>
 #include <string>
@@ -177,12 +179,34 @@ struct Options {
     int time_kernels = 1;
     int tc_min_queries_img = 1;      // f32 with fp16 image: tensor-core filter from the first query
     int tc_min_queries_f32 = 9;     // f32: the FFMA kernel is HBM-bound up to ~16 queries
+    int combine = 1;                 // merge concurrent small host searches into one scan (see Combiner)
     int optimistic = 1;              // enqueue all chunks after the first without host syncs; verify at the end
     int simt_bootstrap = 1;          // threshold-less first chunk runs on the CUDA-core kernel
     int use_shadow = 1;              // f32 index: keep a scaled fp16 image for the tensor-core filter
     int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA
     int tc_cta2 = 1;                 // use the 2-CTA (cta_group::2) kernels when the batch is large enough
     int tc_min_queries = 1;          // int8: the TMA/tcgen05 kernel streams at ~95% of HBM peak even for one query
+};
+
+// Concurrent small searches (the server issues one query per request thread, 16 pool threads:
+// db/connection.rs:235) are combined: while one scan runs, later arrivals queue up and the next
+// scan serves all of them in one pass over the corpus.  Nobody waits when the index is idle.
+struct PendingSearch {
+    const void *queries;
+    int nq;
+    pkv_search_params params;
+    int64_t *out_ids;
+    float *out_dist;
+    int32_t *out_counts;
+    int status = PKV_OK;
+    std::string error;
+    bool done = false;
+};
+struct Combiner {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<PendingSearch *> queue;
+    bool busy = false;
 };
 
 struct Index {
@@ -209,6 +233,8 @@ struct Index {
     std::shared_mutex mu;       // searches shared, append/seal exclusive
     std::mutex ws_mu;
     std::vector<Workspace *> ws_free;
+    Combiner comb;
+    std::atomic<int64_t> n_combined{0};  // searches that shared a scan with another caller
     // counters
     std::atomic<int64_t> n_searches{0}, n_queries{0}, n_launches{0}, n_scan_launches{0}, n_fallback{0};
     double last_scan_ms = 0, last_total_ms = 0;

@@ -268,3 +268,50 @@ def test_dim_mismatch_and_bad_args():
         assert e.value.status == 3
         with pytest.raises(pk.PkvError):
             ix.set_scale_artifact(b"\0\0\0\0")
+
+
+def test_concurrent_searches_from_many_threads():
+    # the reference's read pool runs 16 connection threads (db/connection.rs:235): pkv_search is re-entrant
+    import threading
+
+    x, q, scale, xc, qc = int8_space(60000, 256, 171, 64)
+    want = orc.topk(xc, qc, orc.COSINE, 50, threads=16)
+    with build(xc, pk.I8, scale=scale) as ix:
+        results, errors = [None] * 16, []
+
+        def worker(t):
+            try:
+                sl = slice(t * 4, t * 4 + 4)
+                for _ in range(5):
+                    results[t] = ix.search(qc[sl], 50, pk.COSINE)
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(16)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errors, errors
+        for t in range(16):
+            sl = slice(t * 4, t * 4 + 4)
+            assert_exact(results[t], (want[0][sl], want[1][sl], want[2][sl]))
+
+
+def test_more_queries_than_one_internal_pass():
+    x, q, scale, xc, qc = int8_space(20000, 128, 181, 1500)
+    with build(xc, pk.I8, scale=scale) as ix:
+        assert_exact(ix.search(qc, 10, pk.L2), orc.topk(xc, qc, orc.L2, 10, threads=16))
+    with build(x, pk.F32) as ix:
+        assert_close_topk(ix.search(q, 10, pk.COSINE), orc.topk(x, q, orc.COSINE, 10, threads=16), x, q, orc.COSINE)
+
+
+def test_int8_wide_rows_fall_back_to_cuda_cores():
+    rng = np.random.default_rng(19)
+    xc = rng.integers(-128, 128, size=(3000, 1536), dtype=np.int8)
+    xc[5] = -128
+    xc[6] = 127
+    qc = rng.integers(-128, 128, size=(12, 1536), dtype=np.int8)
+    qc[0] = 127
+    with build(xc, pk.I8) as ix:
+        for metric in METRICS:
+            assert_exact(ix.search(qc, 40, metric), orc.topk(xc, qc, metric, 40, threads=8))
+        assert ix.counters().last_scan_kind == 2
