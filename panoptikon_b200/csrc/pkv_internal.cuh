@@ -185,6 +185,9 @@ struct Options {
     int use_shadow = 1;              // f32 index: keep a scaled fp16 image for the tensor-core filter
     int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA
     int tc_cta2 = 1;                 // use the 2-CTA (cta_group::2) kernels when the batch is large enough
+    int tc_ts = 1;                   // int8, > 128 queries: queries resident in TMEM (pkv_scan_ts.cu)
+    int ts_groups = 2;               // 256-query groups served by one launch of that kernel (row tiles shared through L2)
+    int ts_stages = 0;               // 0 = as many 8 KB row stages as fit
     int tc_min_queries = 1;          // int8: the TMA/tcgen05 kernel streams at ~95% of HBM peak even for one query
 };
 

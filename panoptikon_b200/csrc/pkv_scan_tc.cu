@@ -172,8 +172,11 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // the whole warp runs the loop (warp-uniform addresses and descriptors stay in uniform
+        // registers); one elected lane issues
+        {
             constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, TILE_M, TILE_N);
+            const bool issuer = tc::elect_one();
             tc::mbar_wait(&sh->q_full, 0);
             tc::fence_after_sync();
             uint32_t s = 0, ph = 0, t = 0;
@@ -185,17 +188,19 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
                 for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
-                    const uint32_t a_addr = tc::smem_u32(s_a + (size_t)s * STAGE_BYTES);
-                    const uint32_t b_addr = tc::smem_u32(s_q + (size_t)kc * QCHUNK_BYTES);
+                    const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(s_a) + s * STAGE_BYTES);
+                    const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(s_q) + (uint32_t)kc * QCHUNK_BYTES);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
-                        tc::mma_i8(d_tmem, tc::smem_desc_sw128(a_addr + k * 32), tc::smem_desc_sw128(b_addr + k * 32),
-                                   idesc, (kc | k) != 0);
+                        for (int k = 0; k < CHUNK_BYTES / 32; ++k)
+                            tc::mma_i8(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        tc::mma_commit(&sh->empty[s]);  // stage free once these MMAs have read it
                     }
-                    tc::mma_commit(&sh->empty[s]);  // stage free once these MMAs have read it
+                    __syncwarp();
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
-                tc::mma_commit(&sh->tmem_full[buf]);  // accumulator complete
+                if (issuer) tc::mma_commit(&sh->tmem_full[buf]);  // accumulator complete
+                __syncwarp();
             }
         }
     } else {
@@ -313,6 +318,10 @@ int launch_metric(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, 
 
 int launch_scan_tc2_tile(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, const CUtensorMap &mq, int q0,
                          cudaStream_t s);
+// pkv_scan_ts.cu
+bool scan_ts_supported(const Index &ix);
+int scan_ts_queries_per_launch(const Index &ix);
+int launch_scan_ts(const Index &ix, const ScanArgs &a, int q0, cudaStream_t s);
 
 bool scan_tc_supported(const Index &ix, int nq) {
     if (ix.dtype != PKV_I8 || ix.opt.force_simt) return false;
@@ -331,12 +340,19 @@ int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *laun
     CUtensorMap mrows, mq;
     PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
     PKV_TRY(make_tmap_bytes(&mq, a.queries, (uint64_t)ix.dim_pad, (uint64_t)a.nq, (uint64_t)ix.dim_pad, TILE_N));
-    for (int q0 = 0; q0 < a.nq; q0 += TILE_N) {
+    for (int q0 = 0; q0 < a.nq;) {
         *launches += 1;
-        if (ix.opt.tc_cta2 && a.nq - q0 > TILE_N && (ix.sm_count % 2) == 0) {
+        const int remaining = a.nq - q0;
+        if (remaining > TILE_N && scan_ts_supported(ix)) {
+            // queries resident in TMEM, up to ts_groups x 256 of them per corpus pass
+            PKV_TRY(launch_scan_ts(ix, a, q0, s));
+            q0 += scan_ts_queries_per_launch(ix);
+            continue;
+        }
+        if (ix.opt.tc_cta2 && remaining > TILE_N && (ix.sm_count % 2) == 0) {
             // 256 queries per corpus pass on a CTA pair (cta_group::2)
             PKV_TRY(launch_scan_tc2_tile(ix, a, mrows, mq, q0, s));
-            q0 += TILE_N;
+            q0 += 2 * TILE_N;
             continue;
         }
         switch (a.metric) {
@@ -344,6 +360,7 @@ int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *laun
             case PKV_L2: PKV_TRY(launch_metric<PKV_L2>(ix, a, mrows, mq, q0, kchunks, stages, smem, s)); break;
             default: PKV_TRY(launch_metric<PKV_DOT>(ix, a, mrows, mq, q0, kchunks, stages, smem, s)); break;
         }
+        q0 += TILE_N;
     }
     return PKV_OK;
 }

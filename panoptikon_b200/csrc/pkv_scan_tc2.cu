@@ -169,8 +169,10 @@ scan_i8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (rank == 0 && lane == 0) {
+        // whole warp, warp-uniform descriptors, one elected lane issues (see pkv_scan_tc.cu)
+        if (rank == 0) {
             constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, TILE_ROWS, QN);
+            const bool issuer = tc::elect_one();
             uint32_t s = 0, ph = 0, t = 0;
             for (uint32_t tile = pair; tile < ntiles; tile += npairs, ++t) {
                 const uint32_t buf = t & 1, bph = (t >> 1) & 1;
@@ -180,17 +182,20 @@ scan_i8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_c
                 for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
-                    const uint32_t a_addr = tc::smem_u32(s_a + (size_t)s * STAGE_BYTES);
-                    const uint32_t b_addr = tc::smem_u32(s_q + (size_t)kc * QCHUNK_BYTES);
+                    const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(s_a) + s * STAGE_BYTES);
+                    const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(s_q) + (uint32_t)kc * QCHUNK_BYTES);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
-                        tc::mma_i8_cta2(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
-                                        tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+                        for (int k = 0; k < CHUNK_BYTES / 32; ++k)
+                            tc::mma_i8_cta2(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                            (kc | k) != 0);
+                        tc::mma_commit_cta2(&sh->empty[s]);
                     }
-                    tc::mma_commit_cta2(&sh->empty[s]);
+                    __syncwarp();
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
-                tc::mma_commit_cta2(&sh->tmem_full[buf]);
+                if (issuer) tc::mma_commit_cta2(&sh->tmem_full[buf]);
+                __syncwarp();
             }
         }
     } else {

@@ -199,9 +199,11 @@ scan_float_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // whole warp, warp-uniform descriptors, one elected lane issues (see pkv_scan_tc.cu)
+        {
             constexpr uint32_t idesc = KIND == KIND_TF32 ? tc::make_idesc(/*F32*/ 1, /*TF32*/ 2, TILE_M, NQ)
                                                          : tc::make_idesc(/*F32*/ 1, /*F16*/ 0, TILE_M, NQ);
+            const bool issuer = tc::elect_one();
             uint32_t s = 0, ph = 0, t = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
                 const uint32_t buf = t & 1, bph = (t >> 1) & 1;
@@ -211,21 +213,23 @@ scan_float_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid
                 for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
-                    const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * STAGE);
-                    const uint32_t b_addr = a_addr + A_BYTES;
+                    const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(smem) + s * (uint32_t)STAGE);
+                    const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(smem) + s * (uint32_t)STAGE + A_BYTES);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {  // K = 32 bytes per UMMA: 8 tf32 / 16 f16
-                        if (KIND == KIND_TF32)
-                            tc::mma_tf32(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
-                                         tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
-                        else
-                            tc::mma_f16(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
-                                        tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+                        for (int k = 0; k < CHUNK_BYTES / 32; ++k) {  // K = 32 bytes per UMMA: 8 tf32 / 16 f16
+                            if (KIND == KIND_TF32)
+                                tc::mma_tf32(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                            else
+                                tc::mma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        }
+                        tc::mma_commit(&sh->empty[s]);
                     }
-                    tc::mma_commit(&sh->empty[s]);
+                    __syncwarp();
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
-                tc::mma_commit(&sh->tmem_full[buf]);
+                if (issuer) tc::mma_commit(&sh->tmem_full[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -350,9 +354,11 @@ scan_float_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __gri
             }
         }
     } else if (warp == 1) {
-        if (rank == 0 && lane == 0) {
+        // whole warp, warp-uniform descriptors, one elected lane issues (see pkv_scan_tc.cu)
+        if (rank == 0) {
             constexpr uint32_t idesc = KIND == KIND_TF32 ? tc::make_idesc(/*F32*/ 1, /*TF32*/ 2, 2 * TILE_M, P_NQ)
                                                          : tc::make_idesc(/*F32*/ 1, /*F16*/ 0, 2 * TILE_M, P_NQ);
+            const bool issuer = tc::elect_one();
             uint32_t s = 0, ph = 0, t = 0;
             for (uint32_t tile = pair; tile < ntiles; tile += npairs, ++t) {
                 const uint32_t buf = t & 1, bph = (t >> 1) & 1;
@@ -362,21 +368,25 @@ scan_float_tc2_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __gri
                 for (int kc = 0; kc < kchunks; ++kc) {
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
-                    const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * P_STAGE);
-                    const uint32_t b_addr = a_addr + A_BYTES;
+                    const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(smem) + s * (uint32_t)P_STAGE);
+                    const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(smem) + s * (uint32_t)P_STAGE + A_BYTES);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
-                        if (KIND == KIND_TF32)
-                            tc::mma_tf32_cta2(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
-                                              tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
-                        else
-                            tc::mma_f16_cta2(d_tmem, tc::smem_desc_sw128(a_addr + k * 32),
-                                             tc::smem_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+                        for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
+                            if (KIND == KIND_TF32)
+                                tc::mma_tf32_cta2(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                                  (kc | k) != 0);
+                            else
+                                tc::mma_f16_cta2(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                                 (kc | k) != 0);
+                        }
+                        tc::mma_commit_cta2(&sh->empty[s]);
                     }
-                    tc::mma_commit_cta2(&sh->empty[s]);
+                    __syncwarp();
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
-                tc::mma_commit_cta2(&sh->tmem_full[buf]);
+                if (issuer) tc::mma_commit_cta2(&sh->tmem_full[buf]);
+                __syncwarp();
             }
         }
     } else {

@@ -1,0 +1,350 @@
+// pkv_scan_ts.cu — int8 tensor-core scan with the QUERIES RESIDENT IN TENSOR MEMORY.
+//
+// Same arithmetic and exactness as pkv_scan_tc.cu / pkv_scan_tc2.cu (integer dot products on
+// tcgen05 kind::i8, exact key for the survivors, bit-exact ids and distances); what changes is where
+// the operands live.  With both UMMA operands in shared memory a 256x256 tile moves 96 B/clk of
+// operand reads + 32 B/clk of TMA writes through a 128 B/clk shared memory: the tensor pipe starves.
+// The query tile never changes during a pass, so here it is the A operand and sits in TMEM
+// (tcgen05.mma ... [d_tmem], [a_tmem], b_desc): shared memory only carries the streamed corpus rows
+// (64 B/clk of operand reads + 32 B/clk of TMA writes), and the 96 KB the query tile used to occupy
+// becomes pipeline depth (up to 24 x 8 KB row stages per CTA).
+//
+//   cluster of 2 CTAs (cta_group::2), M = 256 queries (128 per CTA = the 128 TMEM lanes),
+//   N = 128 corpus rows per tile (64 staged by each CTA), K = 32 per instruction.
+//   TMEM columns: [0, dim_pad/4) the CTA's 128 queries (4 int8 per 32-bit column, lane = query),
+//                 [256, 384) and [384, 512) the double-buffered 128 x 128 s32 accumulator
+//                 (lane = query, column = row of the tile).
+//   The accumulator is transposed with respect to pkv_scan_tc2.cu: an epilogue thread owns ONE
+//   query and sees 32 rows per tcgen05.ld, so its pre-filter bound lives in a register.
+//
+// One launch serves up to `groups` x 256 queries: pair p scans for query group p % groups, and the
+// pairs of one tile sequence read the same row tiles at about the same time, so every tile comes
+// from HBM once and from L2 for the other groups.
+//
+// Algorithmic bytes per row per launch: dim_pad (+4 for the row norm); ops: 2 * queries * dim_pad.
+#include "pkv_tc.cuh"
+
+namespace pkv {
+
+namespace {
+
+constexpr int QM_CTA = 128;     // queries per CTA (TMEM lanes)
+constexpr int QM = 256;         // queries per pair (MMA M)
+constexpr int TILE_N = 128;     // corpus rows per tile (MMA N)
+constexpr int ROWS_CTA = 64;    // rows staged by each CTA per tile
+constexpr int CHUNK_BYTES = 128;
+constexpr int STAGE_BYTES = ROWS_CTA * CHUNK_BYTES;  // 8 KiB
+constexpr int MAX_STAGES = 26;
+constexpr int EPI_WARPS = 16;   // lane quarter = warp & 3, 32 accumulator columns each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TS_THREADS = 64 + EPI_THREADS;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COL0 = 256;   // accumulators behind the query columns (dim_pad <= 1024)
+constexpr int HOLD_CAP = 64;
+constexpr int HOLD_FLUSH = 32;
+
+struct TsShared {
+    uint64_t full[MAX_STAGES];
+    uint64_t empty[MAX_STAGES];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    uint32_t hold_cnt[EPI_WARPS];
+    alignas(16) float thr[QM_CTA];
+    alignas(16) int q_mag[QM_CTA];
+    uint32_t hold_row[EPI_WARPS][HOLD_CAP];
+    int hold_dot[EPI_WARPS][HOLD_CAP];
+    uint32_t hold_col[EPI_WARPS][HOLD_CAP];
+};
+
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, M = 256 across the CTA pair
+__device__ __forceinline__ void mma_i8_ts_cta2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Exact filter, exact key, candidate push for one pre-filter survivor (col = query within the CTA).
+template <int METRIC>
+__device__ __noinline__ void consider_ts(const ScanArgs &a, int qbase, int col, int d, uint32_t row, const TsShared *sh) {
+    const int q = qbase + col;
+    if (q >= a.nq || row >= a.row_end) return;
+    const int am = __ldg(a.row_mag_i + row);
+    const int bm = sh->q_mag[col];
+    if (!exact_filter<METRIC>(d, am, bm, sh->thr[col])) return;
+    if (!topk_member(a.topk, q, row)) return;
+    const int8_t *rowp = (const int8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
+    const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
+    topk_push(a.topk, q, row, i8_key(METRIC, d, am, bm, a.dim, rowp, qp));
+}
+
+template <int METRIC>
+__device__ __noinline__ void hold_ts(const ScanArgs &a, int qbase, int col, int d, uint32_t row, TsShared *sh, int ew) {
+    const uint32_t slot = atomicAdd(&sh->hold_cnt[ew], 1u);
+    if (slot < HOLD_CAP) {
+        sh->hold_row[ew][slot] = row;
+        sh->hold_dot[ew][slot] = d;
+        sh->hold_col[ew][slot] = (uint32_t)col;
+    } else {
+        consider_ts<METRIC>(a, qbase, col, d, row, sh);
+    }
+}
+
+template <int METRIC>
+__device__ __forceinline__ void flush_ts(const ScanArgs &a, int qbase, TsShared *sh, int ew, int lane, uint32_t min_cnt) {
+    __syncwarp();
+    const uint32_t cnt = sh->hold_cnt[ew];
+    if (cnt < min_cnt) return;
+    const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
+    for (uint32_t e = lane; e < n; e += 32)
+        consider_ts<METRIC>(a, qbase, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+    __syncwarp();
+    if (lane == 0) sh->hold_cnt[ew] = 0;
+    __syncwarp();
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a, const int q0, const int groups,
+                  const int kchunks, const int stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = tc::smem_u32(smem_raw);
+    uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t *s_b = smem;  // [stages][64 rows][128 B]
+    TsShared *sh = reinterpret_cast<TsShared *>(s_b + (size_t)stages * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const uint32_t grp = pair % (uint32_t)groups, seq = pair / (uint32_t)groups, nseq = npairs / (uint32_t)groups;
+    const int qbase = q0 + (int)grp * QM + (int)rank * QM_CTA;  // first query of this CTA
+    const uint32_t nrows = a.row_end - a.row_begin;
+    const uint32_t ntiles = (nrows + TILE_N - 1) / TILE_N;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            tc::mbar_init(&sh->full[s], 1);
+            tc::mbar_init(&sh->empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&sh->tmem_full[b], 1);
+            tc::mbar_init(&sh->tmem_empty[b], 2 * EPI_WARPS);
+        }
+        for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmap_rows);
+    }
+    if (warp == 1) {
+        tc::tmem_alloc_cta2(&sh->tmem_base, TMEM_COLS);
+        tc::tmem_relinquish_cta2();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    // per-thread query figures (epilogue thread = one query)
+    float tq = 0.f;
+    if (warp >= 2) {
+        const int ew = warp - 2, quarter = warp & 3;
+        const int col = quarter * 32 + lane;
+        const int q = qbase + col;
+        const float thr = q < a.nq ? __ldg(a.topk.thr_f + q) : -__int_as_float(0x7f800000);
+        const int bm = q < a.nq ? __ldg(a.q_mag_i + q) : 0;
+        tq = prefilter_query_figure<METRIC>(thr, bm);
+        if ((ew >> 2) == 0) {
+            sh->thr[col] = thr;
+            sh->q_mag[col] = bm;
+        }
+        // this CTA's 128 queries -> TMEM columns [0, dim_pad/4): lane = query, 4 codes per column.
+        // The four warps of a lane quarter split the K chunks.
+        const int qrow = q < a.nq ? q : (a.nq - 1);  // padding lanes replay a real query; their bound rejects everything
+        const uint8_t *qp = (const uint8_t *)a.queries + (size_t)qrow * a.dim_pad;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int c8 = (ew >> 2); c8 < a.dim_pad / 32; c8 += EPI_WARPS / 4) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32 + 16));
+            const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            tmem_st_32x8(lane_addr + (uint32_t)c8 * 8, v);
+        }
+        tmem_st_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync();  // both CTAs: barriers initialised, TMEM allocated, queries resident
+    tc::fence_after_sync();
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs: own 64 rows of every tile) =====================
+        // whole warp, warp-uniform addresses; one elected lane issues
+        if (seq < nseq) {
+            const bool issuer = tc::elect_one();
+            uint32_t s = 0, ph = 0;
+            const uint32_t full0 = tc::mapa(tc::smem_u32(&sh->full[0]), 0);
+            for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
+                const int row0 = (int)(a.row_begin + tile * TILE_N + rank * ROWS_CTA);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    tc::mbar_wait(&sh->empty[s], ph ^ 1);
+                    if (issuer) {
+                        if (rank == 0) tc::mbar_expect_tx(&sh->full[s], 2 * STAGE_BYTES);  // both CTAs' bytes
+                        tc::tma_load_2d_cta2(s_b + (size_t)s * STAGE_BYTES, &tmap_rows, full0 + s * 8u, kc * CHUNK_BYTES, row0);
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        // The whole warp runs the loop so that every address and descriptor is warp-uniform (uniform
+        // registers, no per-instruction vector->uniform moves); one elected lane issues.
+        if (rank == 0 && seq < nseq) {
+            constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, QM, TILE_N);
+            const bool issuer = tc::elect_one();
+            uint32_t s = 0, ph = 0, t = 0;
+            for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
+                const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+                tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + ACC_COL0 + buf * TILE_N;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    tc::mbar_wait(&sh->full[s], ph);
+                    tc::fence_after_sync();
+                    const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(s_b) + s * STAGE_BYTES);
+                    const uint32_t a_tmem = tmem_base + (uint32_t)kc * (CHUNK_BYTES / 4);
+                    if (issuer) {
+#pragma unroll
+                        for (int k = 0; k < CHUNK_BYTES / 32; ++k)
+                            mma_i8_ts_cta2(d_tmem, a_tmem + k * 8, b_desc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        tc::mma_commit_cta2(&sh->empty[s]);
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+                }
+                if (issuer) tc::mma_commit_cta2(&sh->tmem_full[buf]);
+                __syncwarp();
+            }
+        }
+    } else if (seq < nseq) {
+        // ===================== epilogue (both CTAs: own 128 queries x the tile's 128 rows) =====================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int col0 = (ew >> 2) * 32;           // accumulator columns = rows of the tile
+        const int qcol = quarter * 32 + lane;      // this thread's query within the CTA
+        uint32_t t = 0;
+        // lane j prefetches the norm of row col0 + j (the warp's 32 rows of the tile)
+        uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
+        int am = (seq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
+        const uint32_t empty0 = tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0);
+        const uint32_t empty1 = tc::mapa(tc::smem_u32(&sh->tmem_empty[1]), 0);
+        for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
+            const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
+            const bool row_ok = am >= 0;
+            const int am_min = __reduce_min_sync(0xffffffffu, row_ok ? am : 2147483647);
+            const int am_max = __reduce_max_sync(0xffffffffu, row_ok ? am : 0);
+            nrow = a.row_begin + (tile + nseq) * TILE_N + col0 + lane;
+            am = (tile + nseq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
+            const int bound = prefilter_bound<METRIC>(tq, sqrtf((float)am_min), sqrtf((float)am_max), (float)am_min);
+            tc::mbar_wait(&sh->tmem_full[buf], bph);
+            tc::fence_after_sync();
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ACC_COL0 + buf * TILE_N + col0, v);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(buf ? empty1 : empty0);  // accumulator is in registers
+            // sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once
+            int any = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) any |= bound - (int)v[j] - 1;
+            if (any < 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int d = (int)v[j];
+                    if (d >= bound) hold_ts<METRIC>(a, qbase, qcol, d, row_first + j, sh, ew);
+                }
+            }
+            flush_ts<METRIC>(a, qbase, sh, ew, lane, HOLD_FLUSH);
+        }
+        flush_ts<METRIC>(a, qbase, sh, ew, lane, 1);
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync();  // the peer may still be reading this CTA's row stages / signalling its barriers
+    if (warp == 1) tc::tmem_dealloc_cta2(tmem_base, TMEM_COLS);
+}
+
+template <int METRIC>
+int launch_ts(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, int q0, int groups, int kchunks, int stages,
+              size_t smem, cudaStream_t s) {
+    auto kernel = scan_i8_ts_kernel<METRIC>;
+    PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t ntiles = (a.row_end - a.row_begin + TILE_N - 1) / TILE_N;
+    uint32_t pairs = (uint32_t)ix.sm_count / 2;
+    pairs = pairs / groups * groups;
+    const uint32_t want = ntiles * (uint32_t)groups;  // one tile sequence per tile at most
+    if (pairs > want) pairs = want;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PKV_CUDA(cudaLaunchKernelEx(&cfg, kernel, mrows, a, q0, groups, kchunks, stages));
+    return PKV_OK;
+}
+
+}  // namespace
+
+int scan_ts_queries_per_launch(const Index &ix) {
+    int g = ix.opt.ts_groups;
+    if (g < 1) g = 1;
+    if (g > 4) g = 4;
+    return g * QM;
+}
+
+bool scan_ts_supported(const Index &ix) {
+    return ix.dtype == PKV_I8 && ix.opt.tc_ts && ix.dim_pad <= 1024 && (ix.sm_count % 2) == 0;
+}
+
+// One launch over [row_begin,row_end) for queries [q0, min(nq, q0 + groups*256)).
+int launch_scan_ts(const Index &ix, const ScanArgs &a, int q0, cudaStream_t s) {
+    const int kchunks = ix.dim_pad / CHUNK_BYTES;
+    int groups = (a.nq - q0 + QM - 1) / QM;
+    const int gmax = scan_ts_queries_per_launch(ix) / QM;
+    if (groups > gmax) groups = gmax;
+    if (groups < 1) groups = 1;
+    const size_t ctrl = sizeof(TsShared);
+    int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE_BYTES);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (ix.opt.ts_stages > 1 && ix.opt.ts_stages < stages) stages = ix.opt.ts_stages;
+    const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + ctrl;
+    CUtensorMap mrows;
+    PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, ROWS_CTA));
+    switch (a.metric) {
+        case PKV_COSINE: return launch_ts<PKV_COSINE>(ix, a, mrows, q0, groups, kchunks, stages, smem, s);
+        case PKV_L2: return launch_ts<PKV_L2>(ix, a, mrows, q0, groups, kchunks, stages, smem, s);
+        default: return launch_ts<PKV_DOT>(ix, a, mrows, q0, groups, kchunks, stages, smem, s);
+    }
+}
+
+}  // namespace pkv

@@ -91,3 +91,48 @@ def test_tc_cta_pair_matches_single_cta():
             ix.set_option("tc_cta2", 1)
             assert_exact(pair, single)
             assert_exact(pair, orc.topk(xc, qc, metric, 64, threads=16))
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("nq,groups", [(129, 1), (256, 2), (300, 2), (513, 1), (700, 4), (1024, 2), (1030, 4)])
+def test_ts_queries_in_tmem_bit_exact(metric, nq, groups):
+    # queries resident in TMEM (tcgen05.mma A operand from tensor memory), `groups` x 256 queries per launch
+    x, q, scale, xc, qc = int8_space(60013, 768, 131, nq)
+    with _index(xc, scale) as ix:
+        ix.set_option("ts_groups", groups)
+        ts = ix.search(qc, 100, metric)
+        assert ix.counters().last_scan_kind == 3
+        ix.set_option("tc_ts", 0)
+        ss = ix.search(qc, 100, metric)
+    assert_exact(ts, ss)
+    assert_exact(ts, orc.topk(xc, qc, metric, 100, threads=16))
+
+
+@pytest.mark.parametrize("dim", [8, 100, 512, 1024])
+def test_ts_dims_saturation_zero_rows(dim):
+    rng = np.random.default_rng(17)
+    xc = rng.integers(-128, 128, size=(5000, dim), dtype=np.int8)
+    xc[7] = -128
+    xc[8] = 127
+    xc[9] = 0
+    xc[4999] = 0
+    qc = rng.integers(-128, 128, size=(260, dim), dtype=np.int8)
+    qc[0] = -128
+    qc[1] = 0   # zero query: every cosine is NaN
+    qc[259] = 127
+    with _index(xc) as ix:
+        for metric in METRICS:
+            got = ix.search(qc, 33, metric)
+            assert ix.counters().last_scan_kind == 3
+            assert_exact(got, orc.topk(xc, qc, metric, 33, threads=8))
+
+
+def test_ts_bitmap_and_small_buffers():
+    x, q, scale, xc, qc = int8_space(40000, 256, 141, 200)
+    rng = np.random.default_rng(19)
+    words = (len(xc) + 63) // 64
+    shared = np.packbits(rng.random(words * 64) < 0.2, bitorder="little").view(np.uint64)
+    with _index(xc, scale) as ix:
+        assert_exact(ix.search(qc, 50, pk.L2, bitmap=shared), orc.topk(xc, qc, orc.L2, 50, bitmap=shared, threads=8))
+        ix.set_option("candidate_capacity", 256)   # force range splitting at odd row offsets
+        assert_exact(ix.search(qc, 100, pk.COSINE), orc.topk(xc, qc, orc.COSINE, 100, threads=8))
