@@ -402,7 +402,7 @@ def main():
         "peak": tensor_peak if tensor_bound else hbm_peak,
         "unit": ("TOP/s" if a.dtype == "i8" else "TFLOP/s") if tensor_bound else "GB/s",
         "frac": None, "traffic": None,
-        "kernel": {1: "scan_f32_simt", 2: "scan_i8_simt", 3: "scan_i8_tc (tcgen05 kind::i8)",
+        "kernel": {1: "scan_f32_simt", 2: "scan_i8_simt", 3: "scan_i8_ts (tcgen05 kind::i8, queries resident in TMEM)" if (a.batch > 128 and not any(o.startswith("tc_ts=0") for o in a.opt)) else "scan_i8_tc (tcgen05 kind::i8)",
                    4: "scan_float_tc (tcgen05 kind::tf32 filter on f32 rows + exact rescore)", 5: "scan_f16_simt",
                    6: "scan_float_tc (tcgen05 kind::f16 on f16 rows + exact rescore)",
                    7: "scan_float_tc (tcgen05 kind::f16 filter on the fp16 image of the f32 rows + exact rescore)"
@@ -424,10 +424,18 @@ def main():
     # tile makes one pass per tile, and every pass streams the image again.
     sub = min(a.batch, 1024)
     tiles = (-(-sub // 256) if sub > 128 else 1) if kind in (3, 4, 6, 7) else -(-sub // 8)
+    ratio, note = 1.002, "the ratio ncu measured on the main-chunk launches (profiles/r01_ncu_*.txt)"
+    if kind == 3 and sub > 128 and not any(o.startswith("tc_ts=0") for o in a.opt):
+        # pkv_scan_ts.cu: one launch serves up to 4 groups of 256 queries; the groups share row tiles through L2.
+        # ncu on the main-chunk launch: dram bytes = 1.06x (2 groups) / 1.94x (4 groups) of the rows' bytes
+        # (profiles/r01_ncu_i8_b1024_scan_i8_ts.txt) instead of 2x / 4x for separate passes.
+        groups = min(tiles, 4)
+        tiles = 1
+        ratio = {1: 1.002, 2: 1.06, 3: 1.5, 4: 1.94}[groups]
+        note = f"{groups} query groups per launch share row tiles through L2: ncu measured {ratio}x the rows' bytes per launch"
     roofline["passes_per_step"] = tiles * -(-a.batch // 1024)
-    roofline["traffic"] = roofline["passes_per_step"] * alg_bytes * 1.002
-    roofline["traffic_note"] = ("estimated: passes_per_step x algorithmic bytes x 1.002, the ratio ncu measured on the "
-                                "main-chunk launches (profiles/r01_ncu_*.txt)")
+    roofline["traffic"] = roofline["passes_per_step"] * alg_bytes * ratio
+    roofline["traffic_note"] = "estimated: passes_per_step x algorithmic bytes x " + note
     roofline["frac"] = roofline["achieved"] / roofline["peak"] if roofline["peak"] else None
 
     line = {

@@ -7,7 +7,9 @@
 // The query tile never changes during a pass, so here it is the A operand and sits in TMEM
 // (tcgen05.mma ... [d_tmem], [a_tmem], b_desc): shared memory only carries the streamed corpus rows
 // (64 B/clk of operand reads + 32 B/clk of TMA writes), and the 96 KB the query tile used to occupy
-// becomes pipeline depth (up to 24 x 8 KB row stages per CTA).
+// becomes pipeline depth (~208 KB of row stages per CTA).  A stage holds CPS K-chunks (8 KB boxes)
+// behind ONE barrier: the issuing warp's loop iteration (barrier round trip + issue) costs ~400
+// clocks, an N=128 UMMA runs 64, so a stage must carry >= 8 of them to keep the tensor pipe fed.
 //
 //   cluster of 2 CTAs (cta_group::2), M = 256 queries (128 per CTA = the 128 TMEM lanes),
 //   N = 128 corpus rows per tile (64 staged by each CTA), K = 32 per instruction.
@@ -33,7 +35,7 @@ constexpr int QM = 256;         // queries per pair (MMA M)
 constexpr int TILE_N = 128;     // corpus rows per tile (MMA N)
 constexpr int ROWS_CTA = 64;    // rows staged by each CTA per tile
 constexpr int CHUNK_BYTES = 128;
-constexpr int STAGE_BYTES = ROWS_CTA * CHUNK_BYTES;  // 8 KiB
+constexpr int BOX_BYTES = ROWS_CTA * CHUNK_BYTES;  // one TMA box: 64 rows x 128 B = 8 KiB
 constexpr int MAX_STAGES = 26;
 constexpr int EPI_WARPS = 16;   // lane quarter = warp & 3, 32 accumulator columns each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -114,14 +116,15 @@ __device__ __forceinline__ void flush_ts(const ScanArgs &a, int qbase, TsShared 
     __syncwarp();
 }
 
-template <int METRIC>
+template <int METRIC, int CPS>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a, const int q0, const int groups,
                   const int kchunks, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t *s_b = smem;  // [stages][64 rows][128 B]
+    constexpr int STAGE_BYTES = CPS * BOX_BYTES;
+    uint8_t *s_b = smem;  // [stages][CPS chunks][64 rows][128 B]
     TsShared *sh = reinterpret_cast<TsShared *>(s_b + (size_t)stages * STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,11 +197,16 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             const uint32_t full0 = tc::mapa(tc::smem_u32(&sh->full[0]), 0);
             for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
                 const int row0 = (int)(a.row_begin + tile * TILE_N + rank * ROWS_CTA);
-                for (int kc = 0; kc < kchunks; ++kc) {
+                for (int kc = 0; kc < kchunks; kc += CPS) {
+                    const int n = kchunks - kc < CPS ? kchunks - kc : CPS;  // chunks in this stage
                     tc::mbar_wait(&sh->empty[s], ph ^ 1);
                     if (issuer) {
-                        if (rank == 0) tc::mbar_expect_tx(&sh->full[s], 2 * STAGE_BYTES);  // both CTAs' bytes
-                        tc::tma_load_2d_cta2(s_b + (size_t)s * STAGE_BYTES, &tmap_rows, full0 + s * 8u, kc * CHUNK_BYTES, row0);
+                        if (rank == 0) tc::mbar_expect_tx(&sh->full[s], (uint32_t)(2 * n * BOX_BYTES));  // both CTAs' bytes
+#pragma unroll
+                        for (int j = 0; j < CPS; ++j)
+                            if (j < n)
+                                tc::tma_load_2d_cta2(s_b + (size_t)s * STAGE_BYTES + j * BOX_BYTES, &tmap_rows, full0 + s * 8u,
+                                                     (kc + j) * CHUNK_BYTES, row0);
                     }
                     __syncwarp();
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
@@ -218,15 +226,22 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
                 tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
                 tc::fence_after_sync();
                 const uint32_t d_tmem = tmem_base + ACC_COL0 + buf * TILE_N;
-                for (int kc = 0; kc < kchunks; ++kc) {
+                for (int kc = 0; kc < kchunks; kc += CPS) {
+                    const int n = kchunks - kc < CPS ? kchunks - kc : CPS;
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
                     const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(s_b) + s * STAGE_BYTES);
                     const uint32_t a_tmem = tmem_base + (uint32_t)kc * (CHUNK_BYTES / 4);
                     if (issuer) {
 #pragma unroll
-                        for (int k = 0; k < CHUNK_BYTES / 32; ++k)
-                            mma_i8_ts_cta2(d_tmem, a_tmem + k * 8, b_desc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        for (int j = 0; j < CPS; ++j) {
+                            if (j < n) {
+#pragma unroll
+                                for (int k = 0; k < CHUNK_BYTES / 32; ++k)
+                                    mma_i8_ts_cta2(d_tmem, a_tmem + j * (CHUNK_BYTES / 4) + k * 8,
+                                                   b_desc + (uint64_t)(j * (BOX_BYTES / 16) + k * 2), idesc, (kc | j | k) != 0);
+                            }
+                        }
                         tc::mma_commit_cta2(&sh->empty[s]);
                     }
                     __syncwarp();
@@ -287,10 +302,15 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
     if (warp == 1) tc::tmem_dealloc_cta2(tmem_base, TMEM_COLS);
 }
 
-template <int METRIC>
-int launch_ts(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, int q0, int groups, int kchunks, int stages,
-              size_t smem, cudaStream_t s) {
-    auto kernel = scan_i8_ts_kernel<METRIC>;
+template <int METRIC, int CPS>
+int launch_ts(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, int q0, int groups, int kchunks, cudaStream_t s) {
+    constexpr int STAGE_BYTES = CPS * BOX_BYTES;
+    const size_t ctrl = sizeof(TsShared);
+    int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE_BYTES);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (ix.opt.ts_stages > 1 && ix.opt.ts_stages < stages) stages = ix.opt.ts_stages;
+    const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + ctrl;
+    auto kernel = scan_i8_ts_kernel<METRIC, CPS>;
     PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t ntiles = (a.row_end - a.row_begin + TILE_N - 1) / TILE_N;
     uint32_t pairs = (uint32_t)ix.sm_count / 2;
@@ -333,18 +353,17 @@ int launch_scan_ts(const Index &ix, const ScanArgs &a, int q0, cudaStream_t s) {
     const int gmax = scan_ts_queries_per_launch(ix) / QM;
     if (groups > gmax) groups = gmax;
     if (groups < 1) groups = 1;
-    const size_t ctrl = sizeof(TsShared);
-    int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE_BYTES);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (ix.opt.ts_stages > 1 && ix.opt.ts_stages < stages) stages = ix.opt.ts_stages;
-    const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + ctrl;
     CUtensorMap mrows;
     PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, ROWS_CTA));
-    switch (a.metric) {
-        case PKV_COSINE: return launch_ts<PKV_COSINE>(ix, a, mrows, q0, groups, kchunks, stages, smem, s);
-        case PKV_L2: return launch_ts<PKV_L2>(ix, a, mrows, q0, groups, kchunks, stages, smem, s);
-        default: return launch_ts<PKV_DOT>(ix, a, mrows, q0, groups, kchunks, stages, smem, s);
-    }
+    int cps = ix.opt.ts_chunks > 0 ? ix.opt.ts_chunks : (kchunks % 3 == 0 ? 3 : 2);
+    if (cps > kchunks) cps = kchunks;
+#define PKV_TS_CASE(M, C) \
+    if (a.metric == M && cps == C) return launch_ts<M, C>(ix, a, mrows, q0, groups, kchunks, s)
+    PKV_TS_CASE(PKV_COSINE, 1); PKV_TS_CASE(PKV_COSINE, 2); PKV_TS_CASE(PKV_COSINE, 3); PKV_TS_CASE(PKV_COSINE, 4);
+    PKV_TS_CASE(PKV_L2, 1); PKV_TS_CASE(PKV_L2, 2); PKV_TS_CASE(PKV_L2, 3); PKV_TS_CASE(PKV_L2, 4);
+    PKV_TS_CASE(PKV_DOT, 1); PKV_TS_CASE(PKV_DOT, 2); PKV_TS_CASE(PKV_DOT, 3); PKV_TS_CASE(PKV_DOT, 4);
+#undef PKV_TS_CASE
+    return fail(PKV_ERR_INVALID, "unsupported metric %d / ts_chunks %d", a.metric, cps);
 }
 
 }  // namespace pkv

@@ -136,3 +136,15 @@ def test_ts_bitmap_and_small_buffers():
         assert_exact(ix.search(qc, 50, pk.L2, bitmap=shared), orc.topk(xc, qc, orc.L2, 50, bitmap=shared, threads=8))
         ix.set_option("candidate_capacity", 256)   # force range splitting at odd row offsets
         assert_exact(ix.search(qc, 100, pk.COSINE), orc.topk(xc, qc, orc.COSINE, 100, threads=8))
+
+
+@pytest.mark.parametrize("dim", [128, 640, 768, 1000])
+@pytest.mark.parametrize("chunks", [1, 2, 3, 4])
+def test_ts_chunks_per_stage(dim, chunks):
+    # a stage of the row pipeline holds `chunks` 8 KB K-chunks; rows whose chunk count is not a multiple end on a short stage
+    x, q, scale, xc, qc = int8_space(30011, dim, 151, 257)
+    with _index(xc, scale) as ix:
+        ix.set_option("ts_chunks", chunks)
+        got = ix.search(qc, 40, pk.COSINE)
+        assert ix.counters().last_scan_kind == 3
+    assert_exact(got, orc.topk(xc, qc, orc.COSINE, 40, threads=16))
