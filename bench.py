@@ -233,13 +233,13 @@ def main():
     per = (a.rows + world - 1) // world
     r0, r1 = min(rank * per, a.rows), min((rank + 1) * per, a.rows)
     ix = pk.VectorIndex(a.dim, dtype_code, device=local_rank)
-    ix.reserve(max(r1 - r0, 1))
-    ix.set_row_base(r0)
     if a.force_simt:
         ix.set_option("force_simt", 1)
-    for kv in a.opt:
+    for kv in a.opt:   # before the first allocation: image_mask decides which filter images exist
         name, value = kv.split("=")
         ix.set_option(name, int(value))
+    ix.reserve(max(r1 - r0, 1))
+    ix.set_row_base(r0)
     scale = None
     if a.dtype == "i8":
         # global symmetric absmax scale over the whole corpus (docs/vector-int8-quant.md:11-49)
@@ -383,7 +383,7 @@ def main():
     # the paths that read it).  kind 7 scans the index's fp16 image of the f32 rows.
     pad = lambda n, m: (n + m - 1) // m * m
     row_bytes = {1: a.dim * 4, 2: a.dim + 4, 3: a.dim + 4, 4: a.dim * 4 + 4, 5: a.dim * 2, 6: a.dim * 2 + 4,
-                 7: pad(a.dim, 64) * 2 + 4}.get(kind, a.dim * elem)
+                 7: pad(a.dim, 64) * 2 + 4, 8: pad(a.dim, 128) + 16}.get(kind, a.dim * elem)
     alg_bytes = shard_rows * row_bytes
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
@@ -393,29 +393,31 @@ def main():
     # Which roof binds: passes of <= 128 queries stream the scanned image at HBM speed (ncu: ~85 % DRAM
     # throughput, tensor pipe ~40 % active); 256-query passes keep the tensor pipe ~77 % active with DRAM
     # at ~53 % (profiles/r01_ncu_*), i.e. they are tensor/smem-bound.
-    tensor_bound = kind in (3, 4, 6, 7) and a.batch > 128
+    tensor_bound = kind in (3, 4, 6, 7, 8) and a.batch > 128
+    int8_pipe = a.dtype == "i8" or kind == 8
     bf16_peak = peaks.get("bf16_tflops", 1590.0)   # burst figure: the timed region is a fraction of a second
-    tensor_peak = 2.0 * bf16_peak if a.dtype == "i8" else (0.5 * bf16_peak if kind == 4 else bf16_peak)
+    tensor_peak = 2.0 * bf16_peak if int8_pipe else (0.5 * bf16_peak if kind == 4 else bf16_peak)
     roofline = {
         "bound": "tensor" if tensor_bound else "hbm",
         "achieved": tput if tensor_bound else achieved_gbs,
         "peak": tensor_peak if tensor_bound else hbm_peak,
-        "unit": ("TOP/s" if a.dtype == "i8" else "TFLOP/s") if tensor_bound else "GB/s",
+        "unit": ("TOP/s" if int8_pipe else "TFLOP/s") if tensor_bound else "GB/s",
         "frac": None, "traffic": None,
         "kernel": {1: "scan_f32_simt", 2: "scan_i8_simt", 3: "scan_i8_ts (tcgen05 kind::i8, queries resident in TMEM)" if (a.batch > 128 and not any(o.startswith("tc_ts=0") for o in a.opt)) else "scan_i8_tc (tcgen05 kind::i8)",
                    4: "scan_float_tc (tcgen05 kind::tf32 filter on f32 rows + exact rescore)", 5: "scan_f16_simt",
                    6: "scan_float_tc (tcgen05 kind::f16 on f16 rows + exact rescore)",
-                   7: "scan_float_tc (tcgen05 kind::f16 filter on the fp16 image of the f32 rows + exact rescore)"
+                   7: "scan_float_tc (tcgen05 kind::f16 filter on the fp16 image of the f32 rows + exact rescore)",
+                   8: "scan_img8 (tcgen05 kind::i8 filter on the per-row-scaled int8 image of the rows, queries in TMEM, + exact rescore)"
                    }.get(kind, str(kind)),
         "algorithmic_bytes_per_row": row_bytes,
-        "f32_equivalent_gbs": (shard_rows * a.dim * 4 / (scan_ms_step * 1e-3) / 1e9) if (kind == 7 and scan_ms_step > 0) else None,
+        "f32_equivalent_gbs": (shard_rows * a.dim * 4 / (scan_ms_step * 1e-3) / 1e9) if (kind in (7, 8) and a.dtype == "f32" and scan_ms_step > 0) else None,
         "launches_per_step": scan_launches, "kernel_ms_per_step": scan_ms_step,
         "algorithmic_bytes_per_step": alg_bytes, "algorithmic_ops_per_step": ops,
         "achieved_gbs": achieved_gbs, "achieved_tops": tput,
         "hbm_frac": achieved_gbs / hbm_peak if hbm_peak else None,
         "tensor_frac": tput / tensor_peak if tensor_peak else None,
         "peak_source": peak_src + ("; tensor peak = measured cuBLAS bf16 burst" +
-                                   (" x2 (the int8 pipe runs at twice the bf16 rate; nominal 4500)" if a.dtype == "i8" else "")
+                                   (" x2 (the int8 pipe runs at twice the bf16 rate; nominal 4500)" if int8_pipe else "")
                                    if tensor_bound else ""),
     }
     # DRAM traffic: ncu --set full on the main-chunk launches measured dram__bytes_read+write = 1.0005x
@@ -423,9 +425,9 @@ def main():
     # the launch covers (profiles/r01_ncu_*.txt): no re-reads inside a pass.  A batch wider than one query
     # tile makes one pass per tile, and every pass streams the image again.
     sub = min(a.batch, 1024)
-    tiles = (-(-sub // 256) if sub > 128 else 1) if kind in (3, 4, 6, 7) else -(-sub // 8)
+    tiles = (-(-sub // 256) if sub > 128 else 1) if kind in (3, 4, 6, 7, 8) else -(-sub // 8)
     ratio, note = 1.002, "the ratio ncu measured on the main-chunk launches (profiles/r01_ncu_*.txt)"
-    if kind == 3 and sub > 128 and not any(o.startswith("tc_ts=0") for o in a.opt):
+    if kind in (3, 8) and sub > 128 and not any(o.startswith("tc_ts=0") for o in a.opt):
         # pkv_scan_ts.cu: one launch serves up to 4 groups of 256 queries; the groups share row tiles through L2.
         # ncu on the main-chunk launch: dram bytes = 1.06x (2 groups) / 1.94x (4 groups) of the rows' bytes
         # (profiles/r01_ncu_i8_b1024_scan_i8_ts.txt) instead of 2x / 4x for separate passes.

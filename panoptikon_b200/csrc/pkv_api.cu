@@ -64,6 +64,8 @@ Workspace::~Workspace() {
     cudaFree(d_pend_rows);
     cudaFree(d_pend_cnt);
     cudaFree(d_q16);
+    cudaFree(d_q8);
+    cudaFree(d_q8_meta);
     cudaFree(d_q_scale);
     if (h_status) cudaFreeHost(h_status);
     cudaFree(d_out_ids);
@@ -133,10 +135,13 @@ static int make_workspace(Index &ix, int nq, int k, size_t out_rows, Workspace *
         A((void **)&ws->d_thr_f, sizeof(float) * nq_cap);
         A((void **)&ws->d_status, sizeof(SearchStatus));
         if (ix.dtype != PKV_I8) {
-            A((void **)&ws->d_pend_rows, sizeof(uint32_t) * (size_t)nq_cap * cap);
+            ws->pend_cap = 4 * cap;
+            A((void **)&ws->d_pend_rows, sizeof(uint32_t) * (size_t)nq_cap * ws->pend_cap);
             A((void **)&ws->d_pend_cnt, sizeof(uint32_t) * nq_cap);
             A((void **)&ws->d_q16, sizeof(__half) * (size_t)nq_cap * ix.dim_pad_h);
             A((void **)&ws->d_q_scale, sizeof(float) * nq_cap);
+            A((void **)&ws->d_q8, (size_t)nq_cap * ix.dim_pad8);
+            A((void **)&ws->d_q8_meta, sizeof(float4) * nq_cap);
         }
         A((void **)&ws->d_out_ids, sizeof(int64_t) * out_rows);
         A((void **)&ws->d_out_dist, sizeof(float) * out_rows);
@@ -263,7 +268,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     r.launches = 2;
     r.use_tc = scan_tc_supported(ix, nq);
     r.use_tc_f32 = scan_tc_f32_supported(ix, nq);
-    if (r.use_tc_f32) r.fs = filter_spec_tc_f32(ix, p.metric);
+    if (r.use_tc_f32) r.fs = filter_spec_tc_f32(ix, p.metric, nq);
     ScanArgs &a = r.args;
     a.data = ix.d_data;
     a.pitch_bytes = ix.pitch;
@@ -344,7 +349,7 @@ restart:
     ix.n_scan_launches += r.scan_launches;
     ix.n_fallback += r.depth_overflows;
     ix.last_scan_ms += r.scan_ms;
-    ix.last_scan_kind = r.use_tc_f32 ? scan_tc_f32_kind(ix) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
+    ix.last_scan_kind = r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
     return PKV_OK;
 }
 
@@ -543,9 +548,15 @@ static int grow(Index &ix, int64_t need_rows, bool exact = false) {
     float *nmf = nullptr;
     int64_t *nids = nullptr;
     __half *nsh = nullptr;
+    int8_t *ni8 = nullptr;
+    float4 *nim = nullptr;
     cudaError_t e = cudaMalloc((void **)&nd, (size_t)cap * ix.pitch);
-    if (e == cudaSuccess && ix.dtype == PKV_F32 && ix.opt.use_shadow)
+    if (e == cudaSuccess && ix.dtype == PKV_F32 && (ix.opt.image_mask & 1))
         e = cudaMalloc((void **)&nsh, (size_t)cap * ix.dim_pad_h * sizeof(__half));
+    if (e == cudaSuccess && ix.dtype != PKV_I8 && (ix.opt.image_mask & 2)) {
+        e = cudaMalloc((void **)&ni8, (size_t)cap * ix.dim_pad8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&nim, sizeof(float4) * cap);
+    }
     if (e == cudaSuccess && ix.dtype == PKV_I8) e = cudaMalloc((void **)&nmi, sizeof(int32_t) * cap);
     if (e == cudaSuccess && ix.dtype != PKV_I8) e = cudaMalloc((void **)&nmf, sizeof(float) * cap);
     if (e == cudaSuccess && ix.d_ids) e = cudaMalloc((void **)&nids, sizeof(int64_t) * cap);
@@ -555,6 +566,8 @@ static int grow(Index &ix, int64_t need_rows, bool exact = false) {
         cudaFree(nmf);
         cudaFree(nids);
         cudaFree(nsh);
+        cudaFree(ni8);
+        cudaFree(nim);
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? PKV_ERR_OOM : PKV_ERR_CUDA,
                     "cannot reserve %lld rows (%lld bytes): %s", (long long)cap, (long long)(cap * ix.pitch),
@@ -568,13 +581,23 @@ static int grow(Index &ix, int64_t need_rows, bool exact = false) {
         if (nsh && ix.d_shadow)
             PKV_CUDA(cudaMemcpy(nsh, ix.d_shadow, (size_t)ix.sealed_rows * ix.dim_pad_h * sizeof(__half),
                                 cudaMemcpyDeviceToDevice));
+        if (ni8 && ix.d_img8) {
+            PKV_CUDA(cudaMemcpy(ni8, ix.d_img8, (size_t)ix.sealed_rows * ix.dim_pad8, cudaMemcpyDeviceToDevice));
+            PKV_CUDA(cudaMemcpy(nim, ix.d_img8_meta, sizeof(float4) * ix.sealed_rows, cudaMemcpyDeviceToDevice));
+        }
     }
+    // an image that did not exist before (option changed between appends) is rebuilt for every row at the next seal
+    if ((nsh && !ix.d_shadow) || (ni8 && !ix.d_img8)) ix.image_rows = 0;
     cudaFree(ix.d_data);
     cudaFree(ix.d_mag_i);
     cudaFree(ix.d_mag_f);
     cudaFree(ix.d_ids);
     cudaFree(ix.d_shadow);
+    cudaFree(ix.d_img8);
+    cudaFree(ix.d_img8_meta);
     ix.d_shadow = nsh;
+    ix.d_img8 = ni8;
+    ix.d_img8_meta = nim;
     ix.d_data = nd;
     ix.d_mag_i = nmi;
     ix.d_mag_f = nmf;
@@ -742,6 +765,7 @@ int pkv_index_create(int device, int dim, int dtype, pkv_index **out) {
     ix->dim_pad = pad_dim(dim, dtype);
     ix->pitch = (int64_t)ix->dim_pad * ix->elem;
     ix->dim_pad_h = (dim + 63) / 64 * 64;
+    ix->dim_pad8 = (dim + 127) / 128 * 128;
     ix->sm_count = prop.multiProcessorCount;
     *out = reinterpret_cast<pkv_index *>(ix);
     return PKV_OK;
@@ -757,6 +781,8 @@ int pkv_index_destroy(pkv_index *h) {
     cudaFree(ix->d_mag_i);
     cudaFree(ix->d_mag_f);
     cudaFree(ix->d_shadow);
+    cudaFree(ix->d_img8);
+    cudaFree(ix->d_img8_meta);
     delete ix;
     return PKV_OK;
 }
@@ -833,8 +859,10 @@ int pkv_index_seal(pkv_index *h) {
             }
             PKV_TRY(build_shadow(ix, from, ix.rows, nullptr));
         }
+        if (ix.d_img8) PKV_TRY(build_img8(ix, ix.image_rows < ix.sealed_rows ? ix.image_rows : ix.sealed_rows, ix.rows, nullptr));
         PKV_CUDA(cudaDeviceSynchronize());
         ix.sealed_rows = ix.rows;
+        ix.image_rows = ix.rows;
     }
     return PKV_OK;
 }
@@ -852,7 +880,8 @@ int pkv_index_get_info(const pkv_index *h, pkv_index_info *info) {
     info->scale = ix.scale;
     info->rows = ix.rows;
     info->capacity_rows = ix.cap_rows;
-    info->device_bytes = ix.cap_rows * (ix.pitch + 4 + (ix.d_ids ? 8 : 0) + (ix.d_shadow ? ix.dim_pad_h * 2 : 0));
+    info->device_bytes = ix.cap_rows * (ix.pitch + 4 + (ix.d_ids ? 8 : 0) + (ix.d_shadow ? ix.dim_pad_h * 2 : 0) +
+                                        (ix.d_img8 ? ix.dim_pad8 + 16 : 0));
     info->row_base = ix.row_base;
     return PKV_OK;
 }
@@ -1017,6 +1046,8 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "ts_stages")) ix.opt.ts_stages = (int)value;
     else if (!strcmp(name, "ts_chunks")) ix.opt.ts_chunks = (int)(value < 0 ? 0 : (value > 4 ? 4 : value));
     else if (!strcmp(name, "use_shadow")) ix.opt.use_shadow = (int)value;
+    else if (!strcmp(name, "image_mask")) ix.opt.image_mask = (int)(value & 3);
+    else if (!strcmp(name, "img8_max_queries")) ix.opt.img8_max_queries = (int)value;
     else if (!strcmp(name, "simt_bootstrap")) ix.opt.simt_bootstrap = (int)value;
     else if (!strcmp(name, "optimistic")) ix.opt.optimistic = (int)value;
     else if (!strcmp(name, "combine")) ix.opt.combine = (int)value;

@@ -145,6 +145,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     int nq_cap = 0, dim_pad = 0, cap = 0;
+    int pend_cap = 0;                 // filter survivors per query per chunk (a filter passes several rows per true candidate)
     void *d_qraw = nullptr;       // raw queries as the caller laid them out
     size_t qraw_bytes = 0;
     void *d_q = nullptr;          // padded queries in scan dtype
@@ -154,9 +155,11 @@ struct Workspace {
     uint32_t *d_cnt = nullptr;
     uint64_t *d_thr_key = nullptr;
     float *d_thr_f = nullptr;
-    uint32_t *d_pend_rows = nullptr;  // tf32 path: rows awaiting exact re-scoring, [nq_cap][cap]
+    uint32_t *d_pend_rows = nullptr;  // floating-point filter paths: rows awaiting exact re-scoring, [nq_cap][pend_cap]
     uint32_t *d_pend_cnt = nullptr;
     __half *d_q16 = nullptr;          // fp16-image path: scaled half queries [nq_cap][dim_pad_h]
+    int8_t *d_q8 = nullptr;           // int8-image path: per-query quantised codes [nq_cap][dim_pad8]
+    float4 *d_q8_meta = nullptr;      // {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2} per query
     float *d_q_scale = nullptr;       // accumulator -> dot factor per query
     SearchStatus *d_status = nullptr;
     SearchStatus *h_status = nullptr;  // pinned
@@ -182,7 +185,10 @@ struct Options {
     int combine = 1;                 // merge concurrent small host searches into one scan (see Combiner)
     int optimistic = 1;              // enqueue all chunks after the first without host syncs; verify at the end
     int simt_bootstrap = 1;          // threshold-less first chunk runs on the CUDA-core kernel
-    int use_shadow = 1;              // f32 index: keep a scaled fp16 image for the tensor-core filter
+    int use_shadow = -1;             // which image the tensor-core filter scans: -1 best available, 0 none (tf32 on
+                                     // the f32 rows), 1 fp16 image, 2 int8 image
+    int img8_max_queries = 1 << 30;  // best-available choice: batches above this use the fp16 image when both exist
+    int image_mask = 2;              // images built at seal for f32/f16 indexes: bit 0 fp16 (f32 only), bit 1 int8
     int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA
     int tc_cta2 = 1;                 // use the 2-CTA (cta_group::2) kernels when the batch is large enough
     int tc_ts = 1;                   // int8, > 128 queries: queries resident in TMEM (pkv_scan_ts.cu)
@@ -229,6 +235,11 @@ struct Index {
     __half *d_shadow = nullptr; // f32 index: power-of-two-scaled fp16 image of the rows (filter operand)
     int dim_pad_h = 0;          // components per fp16 image row (multiple of 64)
     float shadow_scale = 0.f;   // 0 = image not built yet
+    int8_t *d_img8 = nullptr;   // f32/f16 index: int8 image, every row quantised with its own scale (filter operand)
+    float4 *d_img8_meta = nullptr;  // per row {|a|/s_a, |codes|, |a - s_a codes|/s_a, 1/s_a}
+    int dim_pad8 = 0;           // bytes per int8 image row (multiple of 128)
+    int64_t image_rows = 0;     // rows whose images are built
+    float img8_U = 0.f;         // code length |a|/s_a of every int8-image row (0 = not fixed yet)
     float shadow_absmax = 0.f;
     bool has_scale = false;
     float scale = 1.0f;
@@ -245,6 +256,13 @@ struct Index {
     int last_scan_kind = 0;
 };
 
+// rows awaiting exact re-scoring (filter kernels of the floating-point paths)
+struct PendDev {
+    uint32_t *rows;  // [nq][cap]
+    uint32_t *cnt;   // [nq]
+    uint32_t cap;
+};
+
 // ---- kernels / launchers (each returns a pkv_status) ----
 // pkv_scan_simt.cu
 int launch_scan_simt(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches);
@@ -253,10 +271,15 @@ bool scan_tc_supported(const Index &ix, int nq);
 int launch_scan_tc(const Index &ix, const ScanArgs &a, cudaStream_t s, int *launches);
 // pkv_scan_tc_f32.cu (tf32 filter + exact re-scoring)
 bool scan_tc_f32_supported(const Index &ix, int nq);
-FilterSpec filter_spec_tc_f32(const Index &ix, int metric);
+FilterSpec filter_spec_tc_f32(const Index &ix, int metric, int nq);
 int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches);
-int scan_tc_f32_kind(const Index &ix);
+int scan_tc_f32_kind(const Index &ix, int nq);
 int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);
+int launch_rescore(const Index &ix, const ScanArgs &a, const PendDev &pend, SearchStatus *status, cudaStream_t s);
+// pkv_scan_img8.cu (int8 image of floating-point rows: tcgen05 kind::i8 filter + exact re-scoring)
+bool img8_usable(const Index &ix);
+int build_img8(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);
+int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches);
 
 // pkv_operator.cu
 int rank_groups(const float *d_dist, int64_t rows, int nq, const int64_t *d_group_of_row, const float *d_weights,

@@ -1,0 +1,682 @@
+// pkv_scan_img8.cu — tensor-core scan of floating-point indexes (f32 / f16 rows) over an INT8 IMAGE:
+// a conservative tcgen05 kind::i8 FILTER plus exact re-scoring of the survivors from the stored rows.
+//
+// Replaces vec_distance_cosine / vec_distance_L2 over `embeddings.embedding` blobs
+// (pql/builder/filters/image_embeddings.rs:321-337, text_embeddings.rs:386-393).  It is the reference's
+// own idea of an int8 "quant" shadow (db/vector_quants.rs:1446-1503, docs/vector-int8-quant.md) turned
+// into a filter whose results stay exact: every score that is reported is computed from the f32 rows
+// by rescore_kernel (pkv_scan_tc_f32.cu) with the same summation order as the CUDA-core scan.
+//
+// Image: every row a is stored as codes c = clamp(rint(a / s_a), -127, 127) with ITS OWN scale s_a = |a| / U,
+// i.e. the DIRECTION of the row is what is quantised: |a|/s_a = U is the same for every row, so a bound that must hold
+// for the 32 rows an epilogue warp sees at once loses nothing to the spread of the rows' scales.  U = 127 / p_ref
+// where p_ref is a high quantile (mean + 1.3 sigma over the first sealed batch) of the rows' peakiness
+// max|a_i| / |a|; components of peakier rows saturate, which only enlarges that row's own error term.  Per row four
+// floats {u = |a|/s_a, v = |c|, w = |a - s_a c|/s_a, r = 1/s_a}.  Queries are quantised per query with
+// s_q = max|q_i| / 127 (e_q = q - s_q c_q).  With acc = c . c_q (exact, s32):
+//     a.q = s_a s_q acc + s_a (c . e_q) + (a - s_a c) . q
+//     |a.q - s_a s_q acc| <= s_a |c| |e_q| + |a - s_a c| |q|                     (Cauchy-Schwarz)
+// A pair can be in the top-k only if a.q >= X(a, q) (X from the exact k-th best distance, per metric), so
+// it may be dropped only if      acc < X / (s_a s_q) - v |e_q|/s_q - w |q|/s_q   (minus rounding slack).
+// For unit-norm 768-d Gaussian-like data the slack is ~1.5 % of |a||q|: ~5 survivors per true top-k row.
+//
+// Kernel = the int8 scan with the queries resident in TMEM (pkv_scan_ts.cu): A = 128 queries per CTA in
+// tensor memory, B = row tiles streamed by TMA, accumulator lane = query / column = row.  Two shapes:
+//   PAIR   cta_group::2, M = 256 queries, each CTA stages 64 rows of a 128-row tile; up to 4 query groups
+//          per launch share row tiles through L2                                    (batches > 128)
+//   single cta_group::1, M = 128 queries, one CTA per SM stages whole 128-row tiles  (batches <= 128:
+//          HBM-bound, half the bytes of the fp16 image and a quarter of the f32 rows)
+//
+// Algorithmic bytes per row per pass: dim_pad8 (+16 B row figures); ops: 2 * queries * dim_pad8.
+#include "pkv_tc.cuh"
+
+namespace pkv {
+
+namespace {
+
+constexpr int QM_CTA = 128;
+constexpr int TILE_N = 128;
+constexpr int CHUNK_BYTES = 128;
+constexpr int MAX_STAGES = 26;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int IMG_THREADS = 64 + EPI_THREADS;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COL0 = 256;
+constexpr int HOLD_CAP = 64;
+constexpr int HOLD_FLUSH = 32;
+constexpr float BOUND_CLAMP = 1.07e9f;
+
+struct ImgArgs {
+    const float4 *row_meta;  // [rows] {|a|/s_a, |c|, |a - s_a c|/s_a, 1/s_a}
+    const int8_t *q8;        // [nq][dim_pad8] query codes
+    const float4 *q_meta;    // [nq] {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2}
+    PendDev pend;
+    int dim_pad8;
+};
+
+struct ImgShared {
+    uint64_t full[MAX_STAGES];
+    uint64_t empty[MAX_STAGES];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    uint32_t hold_cnt[EPI_WARPS];
+    alignas(16) float4 qc[QM_CTA];  // per query {c1, c2, ty, tz}
+    float qs[QM_CTA];               // per query: extra slack per unit of x2 (L2: rounding of |q|^2 and of the threshold)
+    uint32_t hold_row[EPI_WARPS][HOLD_CAP];
+    int hold_dot[EPI_WARPS][HOLD_CAP];
+    uint32_t hold_col[EPI_WARPS][HOLD_CAP];
+};
+
+// Bound on acc below which a pair is certainly outside the top-k:   lead(row, query) - ty*v - tz*w - slack
+//   COSINE  lead = c1 * x1,          x1 = |a|/s_a,               c1 = -thr_f/s_q
+//   DOT     lead = c1 * x1,          x1 = 1/s_a,                 c1 = -thr_f/s_q
+//   L2      lead = c1 * x2 * (x1 + c2),  x1 = |a|^2/2, x2 = 1/s_a,   c1 = 1/s_q, c2 = (|q|^2 - thr_f)/2
+// (L2 keeps the product form: bounding |a|^2/(2 s_a) and (|q|^2 - thr_f)/(2 s_a) separately over a warp's rows
+// would subtract two loosened terms of almost equal size.)
+template <int METRIC>
+__device__ __forceinline__ void row_figures(const float4 m, float &x1, float &x2) {
+    x2 = m.w;
+    if (METRIC == PKV_COSINE) x1 = m.x;
+    else if (METRIC == PKV_DOT) x1 = m.w;
+    else {
+        const float na = m.x / m.w;  // |a|
+        x1 = 0.5f * na * na;
+    }
+}
+
+// [x1lo, x1hi], [x2lo, x2hi]: range of the row figures over the rows the bound must hold for (a single row: lo = hi);
+// v, w, u: their largest |c|, |a - s_a c|/s_a, |a|/s_a.  Rounding slack: 3e-5 relative on every term (row and query
+// figures are good to ~1e-5), qs per unit of x2 (L2: |q|^2 is a sequential f32 sum), 4e-6 |a||q|/(s_a s_q) (the
+// re-scorer's own f32 summation), + 1.
+template <int METRIC>
+__device__ __forceinline__ float pair_bound(const float4 qc, float qs, float x1lo, float x1hi, float x2lo, float x2hi,
+                                            float v, float w, float u) {
+    float lead, mag;
+    if (METRIC == PKV_L2) {
+        const float sum = x1lo + qc.y;  // smallest |a|^2/2 + (|q|^2 - thr)/2 over the rows
+        lead = qc.x * (sum >= 0.f ? x2lo : x2hi) * sum;
+        mag = qc.x * x2hi * (x1hi + fabsf(qc.y));
+    } else {
+        lead = qc.x * (qc.x >= 0.f ? x1lo : x1hi);
+        mag = fabsf(qc.x) * x1hi;
+    }
+    const float neg = qc.z * v + qc.w * w;
+    return lead - neg - (3e-5f * (mag + neg) + qs * x2hi + 4e-6f * qc.w * u + 1.0f);
+}
+
+// One pre-filter survivor: exact per-pair bound, membership, then park the row for exact re-scoring.
+template <int METRIC>
+__device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, int qbase, int col, int d, uint32_t row,
+                                          const ImgShared *sh) {
+    const int q = qbase + col;
+    if (q >= a.nq || row >= a.row_end) return;
+    const float4 m = __ldg(im.row_meta + row);
+    float x1, x2;
+    row_figures<METRIC>(m, x1, x2);
+    const float b = pair_bound<METRIC>(sh->qc[col], sh->qs[col], x1, x1, x2, x2, m.y, m.z, m.x);
+    if ((float)d < b) return;  // NaN bound (non-finite row or query): kept
+    if (!topk_member(a.topk, q, row)) return;
+    const uint32_t slot = atomicAdd(im.pend.cnt + q, 1u);
+    if (slot < im.pend.cap) im.pend.rows[(size_t)q * im.pend.cap + slot] = row;
+}
+
+template <int METRIC>
+__device__ __noinline__ void hold_img(const ScanArgs &a, const ImgArgs &im, int qbase, int col, int d, uint32_t row,
+                                      ImgShared *sh, int ew) {
+    const uint32_t slot = atomicAdd(&sh->hold_cnt[ew], 1u);
+    if (slot < HOLD_CAP) {
+        sh->hold_row[ew][slot] = row;
+        sh->hold_dot[ew][slot] = d;
+        sh->hold_col[ew][slot] = (uint32_t)col;
+    } else {
+        consider_img<METRIC>(a, im, qbase, col, d, row, sh);
+    }
+}
+
+template <int METRIC>
+__device__ __forceinline__ void flush_img(const ScanArgs &a, const ImgArgs &im, int qbase, ImgShared *sh, int ew, int lane,
+                                          uint32_t min_cnt) {
+    __syncwarp();
+    const uint32_t cnt = sh->hold_cnt[ew];
+    if (cnt < min_cnt) return;
+    const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
+    for (uint32_t e = lane; e < n; e += 32)
+        consider_img<METRIC>(a, im, qbase, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+    __syncwarp();
+    if (lane == 0) sh->hold_cnt[ew] = 0;
+    __syncwarp();
+}
+
+// non-negative floats order like their bit patterns: hardware warp min/max on the unsigned view
+__device__ __forceinline__ float warp_min_nn(float v) {
+    return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+__device__ __forceinline__ float warp_max_nn(float v) {
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+}
+
+template <int METRIC, int CPS, bool PAIR>
+__global__ void __launch_bounds__(IMG_THREADS, 1)
+scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a, const ImgArgs im, const int q0,
+                 const int groups, const int kchunks, const int stages) {
+    constexpr int ROWS_CTA = PAIR ? 64 : 128;          // rows this CTA stages per tile
+    constexpr int BOX_BYTES = ROWS_CTA * CHUNK_BYTES;  // one TMA box
+    constexpr int STAGE_BYTES = CPS * BOX_BYTES;
+    constexpr int NCTA = PAIR ? 2 : 1;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = tc::smem_u32(smem_raw);
+    uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t *s_b = smem;  // [stages][CPS chunks][ROWS_CTA rows][128 B]
+    ImgShared *sh = reinterpret_cast<ImgShared *>(s_b + (size_t)stages * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
+    const uint32_t unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x, nunits = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    const uint32_t grp = unit % (uint32_t)groups, seq = unit / (uint32_t)groups, nseq = nunits / (uint32_t)groups;
+    const int qbase = q0 + (int)grp * (NCTA * QM_CTA) + (int)rank * QM_CTA;  // first query of this CTA
+    const uint32_t nrows = a.row_end - a.row_begin;
+    const uint32_t ntiles = (nrows + TILE_N - 1) / TILE_N;
+    const float INF = __int_as_float(0x7f800000);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            tc::mbar_init(&sh->full[s], 1);
+            tc::mbar_init(&sh->empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&sh->tmem_full[b], 1);
+            tc::mbar_init(&sh->tmem_empty[b], NCTA * EPI_WARPS);
+        }
+        for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmap_rows);
+    }
+    if (warp == 1) {
+        if (PAIR) {
+            tc::tmem_alloc_cta2(&sh->tmem_base, TMEM_COLS);
+            tc::tmem_relinquish_cta2();
+        } else {
+            tc::tmem_alloc(&sh->tmem_base, TMEM_COLS);
+            tc::tmem_relinquish();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    float4 qc = make_float4(0.f, 0.f, 0.f, 0.f);  // this thread's query (epilogue thread = one query)
+    float qs = 0.f;
+    bool live = false;  // padded query lanes keep nothing
+    if (warp >= 2) {
+        const int ew = warp - 2, quarter = warp & 3;
+        const int col = quarter * 32 + lane;
+        const int q = qbase + col;
+        if (q < a.nq) {
+            live = true;
+            const float thr = __ldg(a.topk.thr_f + q);  // +inf while the query has no threshold: keep everything
+            const float4 qm = __ldg(im.q_meta + q);
+            if (METRIC == PKV_L2) {
+                qc.x = qm.x;
+                qc.y = 0.5f * (qm.w - thr);
+                qs = 1e-4f * 0.5f * qm.x * (qm.w + fabsf(thr));  // |q|^2 is a sequential f32 sum: good to ~6e-5
+            } else {
+                qc.x = -thr * qm.x;
+                qc.y = 0.f;
+            }
+            qc.z = qm.y;
+            qc.w = qm.z;
+        }
+        if ((ew >> 2) == 0) {
+            sh->qc[col] = qc;
+            sh->qs[col] = qs;
+        }
+        // this CTA's 128 queries -> TMEM columns [0, dim_pad8/4): lane = query, 4 codes per column
+        const int qrow = q < a.nq ? q : (a.nq - 1);
+        const uint8_t *qp = (const uint8_t *)im.q8 + (size_t)qrow * im.dim_pad8;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int c8 = (ew >> 2); c8 < im.dim_pad8 / 32; c8 += EPI_WARPS / 4) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32 + 16));
+            const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            tc::tmem_st_32x8(lane_addr + (uint32_t)c8 * 8, v);
+        }
+        tc::tmem_st_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (PAIR) tc::cluster_sync();
+    tc::fence_after_sync();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (seq < nseq) {
+            const bool issuer = tc::elect_one();
+            uint32_t s = 0, ph = 0;
+            const uint32_t full0 = PAIR ? tc::mapa(tc::smem_u32(&sh->full[0]), 0) : tc::smem_u32(&sh->full[0]);
+            for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
+                const int row0 = (int)(a.row_begin + tile * TILE_N + rank * ROWS_CTA);
+                for (int kc = 0; kc < kchunks; kc += CPS) {
+                    const int n = kchunks - kc < CPS ? kchunks - kc : CPS;
+                    tc::mbar_wait(&sh->empty[s], ph ^ 1);
+                    if (issuer) {
+                        if (rank == 0) tc::mbar_expect_tx(&sh->full[s], (uint32_t)(NCTA * n * BOX_BYTES));
+#pragma unroll
+                        for (int j = 0; j < CPS; ++j) {
+                            if (j < n) {
+                                uint8_t *dst = s_b + (size_t)s * STAGE_BYTES + j * BOX_BYTES;
+                                if (PAIR)
+                                    tc::tma_load_2d_cta2(dst, &tmap_rows, full0 + s * 8u, (kc + j) * CHUNK_BYTES, row0);
+                                else
+                                    tc::tma_load_2d(dst, &tmap_rows, &sh->full[s], (kc + j) * CHUNK_BYTES, row0);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+        if (rank == 0 && seq < nseq) {
+            constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, NCTA * QM_CTA, TILE_N);
+            const bool issuer = tc::elect_one();
+            uint32_t s = 0, ph = 0, t = 0;
+            for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
+                const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+                tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + ACC_COL0 + buf * TILE_N;
+                for (int kc = 0; kc < kchunks; kc += CPS) {
+                    const int n = kchunks - kc < CPS ? kchunks - kc : CPS;
+                    tc::mbar_wait(&sh->full[s], ph);
+                    tc::fence_after_sync();
+                    const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(s_b) + s * STAGE_BYTES);
+                    const uint32_t a_tmem = tmem_base + (uint32_t)kc * (CHUNK_BYTES / 4);
+                    if (issuer) {
+#pragma unroll
+                        for (int j = 0; j < CPS; ++j) {
+                            if (j < n) {
+#pragma unroll
+                                for (int k = 0; k < CHUNK_BYTES / 32; ++k) {
+                                    const uint32_t at = a_tmem + j * (CHUNK_BYTES / 4) + k * 8;
+                                    const uint64_t bd = b_desc + (uint64_t)(j * (BOX_BYTES / 16) + k * 2);
+                                    if (PAIR) tc::mma_i8_ts_cta2(d_tmem, at, bd, idesc, (kc | j | k) != 0);
+                                    else tc::mma_i8_ts(d_tmem, at, bd, idesc, (kc | j | k) != 0);
+                                }
+                            }
+                        }
+                        if (PAIR) tc::mma_commit_cta2(&sh->empty[s]);
+                        else tc::mma_commit(&sh->empty[s]);
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+                }
+                if (issuer) {
+                    if (PAIR) tc::mma_commit_cta2(&sh->tmem_full[buf]);
+                    else tc::mma_commit(&sh->tmem_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (seq < nseq) {
+        // ===================== epilogue: own 128 queries x the tile's 128 rows =====================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int col0 = (ew >> 2) * 32;       // accumulator columns = rows of the tile
+        const int qcol = quarter * 32 + lane;  // this thread's query within the CTA
+        uint32_t t = 0;
+        // lane j prefetches the figures of row col0 + j (the warp's 32 rows of the tile)
+        uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
+        bool row_ok = seq < ntiles && nrow < a.row_end;
+        float4 m = row_ok ? __ldg(im.row_meta + nrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t empty0 = PAIR ? tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0) : tc::smem_u32(&sh->tmem_empty[0]);
+        const uint32_t empty1 = PAIR ? tc::mapa(tc::smem_u32(&sh->tmem_empty[1]), 0) : tc::smem_u32(&sh->tmem_empty[1]);
+        for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
+            const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
+            // loosest figures over the warp's 32 rows (rows past the end must not loosen them)
+            float x1, x2;
+            row_figures<METRIC>(m, x1, x2);
+            const float x1lo = warp_min_nn(row_ok ? x1 : INF), x1hi = warp_max_nn(row_ok ? x1 : 0.f);
+            float x2lo = 0.f, x2hi = 0.f;
+            if (METRIC == PKV_L2) {
+                x2lo = warp_min_nn(row_ok ? x2 : INF);
+                x2hi = warp_max_nn(row_ok ? x2 : 0.f);
+            }
+            const float vhi = warp_max_nn(m.y), whi = warp_max_nn(m.z), uhi = warp_max_nn(m.x);
+            nrow = a.row_begin + (tile + nseq) * TILE_N + col0 + lane;
+            row_ok = tile + nseq < ntiles && nrow < a.row_end;
+            m = row_ok ? __ldg(im.row_meta + nrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float bf = pair_bound<METRIC>(qc, qs, x1lo, x1hi, x2lo, x2hi, vhi, whi, uhi);
+            bf = fminf(fmaxf(bf, -BOUND_CLAMP), BOUND_CLAMP);  // NaN -> -clamp: keep everything
+            const int bound = live ? __float2int_rd(bf) : (int)BOUND_CLAMP;
+            tc::mbar_wait(&sh->tmem_full[buf], bph);
+            tc::fence_after_sync();
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ACC_COL0 + buf * TILE_N + col0, v);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR) tc::mbar_arrive_cluster(buf ? empty1 : empty0);  // accumulator is in registers
+                else tc::mbar_arrive(&sh->tmem_empty[buf]);
+            }
+            // sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once
+            int any = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) any |= bound - (int)v[j] - 1;
+            if (any < 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int d = (int)v[j];
+                    if (d >= bound) hold_img<METRIC>(a, im, qbase, qcol, d, row_first + j, sh, ew);
+                }
+            }
+            flush_img<METRIC>(a, im, qbase, sh, ew, lane, HOLD_FLUSH);
+        }
+        flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (PAIR) tc::cluster_sync();
+    if (warp == 1) {
+        if (PAIR) tc::tmem_dealloc_cta2(tmem_base, TMEM_COLS);
+        else tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Image of rows [row_begin, row_end): one warp per row.
+template <bool ROWS_F16>
+__global__ void __launch_bounds__(256) img8_build_kernel(const uint8_t *data, int64_t pitch, int dim, int dim_pad8,
+                                                         int64_t row_begin, int64_t row_end, float U, int8_t *img,
+                                                         float4 *meta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= row_end) return;
+    const uint8_t *src = data + (size_t)row * (size_t)pitch;
+    auto load = [&](int i) -> float {
+        return ROWS_F16 ? __half2float(reinterpret_cast<const __half *>(src)[i]) : reinterpret_cast<const float *>(src)[i];
+    };
+    float amax = 0.f, nrm2 = 0.f;
+    bool bad = false;
+    for (int i = lane; i < dim; i += 32) {
+        const float x = load(i);
+        const float ax = fabsf(x);
+        if (!(ax <= 3.0e38f)) bad = true;  // NaN or inf
+        amax = fmaxf(amax, ax);
+        nrm2 = fmaf(x, x, nrm2);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+    }
+    bad = __any_sync(0xffffffffu, bad) || !(nrm2 <= 3.0e38f);
+    float s = sqrtf(nrm2) / U;
+    if (!(s > 0.f) || bad) s = 1.0f;  // zero row (codes 0, no error) or non-finite row (flagged below)
+    const float r = 1.0f / s;
+    if (!(r <= 3.0e38f)) bad = true;  // denormal scale: treat as unfilterable
+    int8_t *dst = img + (size_t)row * dim_pad8;
+    float err2 = 0.f;
+    int cn2 = 0;
+    for (int i0 = lane * 4; i0 < dim_pad8; i0 += 128) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            int c = 0;
+            if (i < dim && !bad) {
+                const float x = load(i);
+                float t = rintf(__fdiv_rn(x, s));
+                t = fminf(fmaxf(t, -127.f), 127.f);
+                c = (int)t;
+                const float ev = fmaf(-s, t, x);
+                err2 = fmaf(ev, ev, err2);
+                cn2 += c * c;
+            }
+            packed |= ((uint32_t)(uint8_t)(int8_t)c) << (8 * e);
+        }
+        *reinterpret_cast<uint32_t *>(dst + i0) = packed;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+        cn2 += __shfl_xor_sync(0xffffffffu, cn2, o);
+    }
+    if (lane == 0) {
+        float4 m;
+        if (bad) {
+            m = make_float4(0.f, 0.f, __int_as_float(0x7f800000), 1.0f);  // w = +inf: the bound is -inf/NaN, always re-scored
+        } else {
+            m.x = sqrtf(nrm2) * r;
+            m.y = sqrtf((float)cn2);
+            m.z = sqrtf(err2) * 1.0001f * r;
+            m.w = r;
+            if (!(m.x <= 3.0e38f) || !(m.z <= 3.0e38f)) m = make_float4(0.f, 0.f, __int_as_float(0x7f800000), 1.0f);
+        }
+        meta[row] = m;
+    }
+}
+
+// Peakiness statistics of rows [row_begin, row_end): sum, sum of squares and count of max|a_i| / |a| over the
+// finite non-zero rows (one warp per row).
+template <bool ROWS_F16>
+__global__ void __launch_bounds__(256) img8_stats_kernel(const uint8_t *data, int64_t pitch, int dim, int64_t row_begin,
+                                                         int64_t row_end, double *stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= row_end) return;
+    const uint8_t *src = data + (size_t)row * (size_t)pitch;
+    float amax = 0.f, nrm2 = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float x = ROWS_F16 ? __half2float(reinterpret_cast<const __half *>(src)[i]) : reinterpret_cast<const float *>(src)[i];
+        amax = fmaxf(amax, fabsf(x));
+        nrm2 = fmaf(x, x, nrm2);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+    }
+    if (lane == 0 && nrm2 > 0.f && nrm2 <= 3.0e38f && amax <= 3.0e38f) {
+        const double p = (double)amax / sqrt((double)nrm2);
+        atomicAdd(stats + 0, p);
+        atomicAdd(stats + 1, p * p);
+        atomicAdd(stats + 2, 1.0);
+    }
+}
+
+// Query codes and figures: one warp per query, from the padded f32 queries of the workspace.
+__global__ void __launch_bounds__(256) img8_prep_queries_kernel(const float *q, int nq, int dim, int dim_pad, int dim_pad8,
+                                                                const float *q_mag_f, int8_t *q8, float4 *q_meta) {
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const float *src = q + (size_t)qi * dim_pad;
+    float amax = 0.f, nrm2 = 0.f;
+    bool bad = false;
+    for (int i = lane; i < dim; i += 32) {
+        const float x = src[i];
+        const float ax = fabsf(x);
+        if (!(ax <= 3.0e38f)) bad = true;
+        amax = fmaxf(amax, ax);
+        nrm2 = fmaf(x, x, nrm2);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+    }
+    bad = __any_sync(0xffffffffu, bad) || !(nrm2 <= 3.0e38f);
+    float s = amax / 127.0f;
+    if (!(s > 0.f) || bad) s = 1.0f;
+    const float r = 1.0f / s;
+    if (!(r <= 3.0e38f)) bad = true;
+    int8_t *dst = q8 + (size_t)qi * dim_pad8;
+    float err2 = 0.f;
+    for (int i0 = lane * 4; i0 < dim_pad8; i0 += 128) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            int c = 0;
+            if (i < dim && !bad) {
+                const float x = src[i];
+                float t = rintf(__fdiv_rn(x, s));
+                t = fminf(fmaxf(t, -127.f), 127.f);
+                c = (int)t;
+                const float ev = fmaf(-s, t, x);
+                err2 = fmaf(ev, ev, err2);
+            }
+            packed |= ((uint32_t)(uint8_t)(int8_t)c) << (8 * e);
+        }
+        *reinterpret_cast<uint32_t *>(dst + i0) = packed;
+    }
+    for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+    if (lane == 0) {
+        const float INF = __int_as_float(0x7f800000);
+        float4 m;
+        m.x = r;
+        m.y = bad ? INF : sqrtf(err2) * 1.0001f * r;
+        m.z = bad ? INF : sqrtf(nrm2) * 1.00001f * r;
+        m.w = q_mag_f[qi];  // the |q|^2 the thresholds and the re-scorer use
+        q_meta[qi] = m;
+    }
+}
+
+template <int METRIC, int CPS, bool PAIR>
+int launch_img8(const Index &ix, const ScanArgs &a, const ImgArgs &im, const CUtensorMap &mrows, int q0, int groups,
+                int kchunks, cudaStream_t s) {
+    constexpr int STAGE_BYTES = CPS * (PAIR ? 64 : 128) * CHUNK_BYTES;
+    const size_t ctrl = sizeof(ImgShared);
+    int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE_BYTES);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (ix.opt.ts_stages > 1 && ix.opt.ts_stages < stages) stages = ix.opt.ts_stages;
+    const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + ctrl;
+    auto kernel = scan_img8_kernel<METRIC, CPS, PAIR>;
+    PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t ntiles = (a.row_end - a.row_begin + TILE_N - 1) / TILE_N;
+    uint32_t units = PAIR ? (uint32_t)ix.sm_count / 2 : (uint32_t)ix.sm_count;
+    units = units / groups * groups;
+    const uint32_t want = ntiles * (uint32_t)groups;
+    if (units > want) units = want;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(PAIR ? 2 * units : units);
+    cfg.blockDim = dim3(IMG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PKV_CUDA(cudaLaunchKernelEx(&cfg, kernel, mrows, a, im, q0, groups, kchunks, stages));
+    return PKV_OK;
+}
+
+template <int METRIC>
+int launch_img8_metric(const Index &ix, const ScanArgs &a, const ImgArgs &im, const CUtensorMap &m64,
+                       const CUtensorMap &m128, int kchunks, cudaStream_t s, int *launches) {
+    const int cps = (kchunks % 3 == 0) ? 3 : 2;
+    const bool pairs_ok = (ix.sm_count % 2) == 0 && ix.opt.tc_cta2;
+    int gmax = ix.opt.ts_groups;
+    if (gmax < 1) gmax = 1;
+    if (gmax > 4) gmax = 4;
+    for (int q0 = 0; q0 < a.nq;) {
+        const int left = a.nq - q0;
+        *launches += 1;
+        if (left > QM_CTA && pairs_ok) {
+            int groups = (left + 2 * QM_CTA - 1) / (2 * QM_CTA);
+            if (groups > gmax) groups = gmax;
+            if (cps == 3) PKV_TRY((launch_img8<METRIC, 3, true>(ix, a, im, m64, q0, groups, kchunks, s)));
+            else PKV_TRY((launch_img8<METRIC, 2, true>(ix, a, im, m64, q0, groups, kchunks, s)));
+            q0 += groups * 2 * QM_CTA;
+        } else {
+            if (cps == 3) PKV_TRY((launch_img8<METRIC, 3, false>(ix, a, im, m128, q0, 1, kchunks, s)));
+            else PKV_TRY((launch_img8<METRIC, 2, false>(ix, a, im, m128, q0, 1, kchunks, s)));
+            q0 += QM_CTA;
+        }
+    }
+    return PKV_OK;
+}
+
+}  // namespace
+
+bool img8_usable(const Index &ix) {
+    return ix.d_img8 && ix.d_img8_meta && ix.dim_pad8 <= 1024 && ix.image_rows >= ix.sealed_rows &&
+           (ix.dtype == PKV_F32 || ix.dtype == PKV_F16);
+}
+
+int build_img8(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) {
+    if (row_end <= row_begin || !ix.d_img8) return PKV_OK;
+    const int warps = 8;
+    if (ix.img8_U == 0.f) {
+        // fix the code length U = |a|/s_a of the index from the peakiness of (a sample of) the first sealed batch
+        int64_t sample_end = row_end - row_begin > 262144 ? row_begin + 262144 : row_end;
+        double *d_stats = nullptr, h[3] = {0, 0, 0};
+        PKV_CUDA(cudaMalloc((void **)&d_stats, 3 * sizeof(double)));
+        PKV_CUDA(cudaMemsetAsync(d_stats, 0, 3 * sizeof(double), s));
+        const int64_t sb = (sample_end - row_begin + warps - 1) / warps;
+        if (ix.dtype == PKV_F16)
+            img8_stats_kernel<true><<<(unsigned)sb, warps * 32, 0, s>>>(ix.d_data, ix.pitch, ix.dim, row_begin, sample_end, d_stats);
+        else
+            img8_stats_kernel<false><<<(unsigned)sb, warps * 32, 0, s>>>(ix.d_data, ix.pitch, ix.dim, row_begin, sample_end, d_stats);
+        cudaError_t e = cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_stats);
+        PKV_CUDA(e);
+        double p_ref = 1.0;  // no usable row yet: one-hot rows would still fit
+        if (h[2] > 0) {
+            const double mean = h[0] / h[2];
+            double var = h[1] / h[2] - mean * mean;
+            if (var < 0) var = 0;
+            p_ref = mean + 1.3 * sqrt(var);
+            if (p_ref > 1.0) p_ref = 1.0;
+            if (p_ref < 1e-3) p_ref = 1e-3;
+        }
+        ix.img8_U = (float)(127.0 / p_ref);
+    }
+    const int64_t blocks = (row_end - row_begin + warps - 1) / warps;
+    if (ix.dtype == PKV_F16)
+        img8_build_kernel<true><<<(unsigned)blocks, warps * 32, 0, s>>>(ix.d_data, ix.pitch, ix.dim, ix.dim_pad8, row_begin,
+                                                                        row_end, ix.img8_U, ix.d_img8, ix.d_img8_meta);
+    else
+        img8_build_kernel<false><<<(unsigned)blocks, warps * 32, 0, s>>>(ix.d_data, ix.pitch, ix.dim, ix.dim_pad8, row_begin,
+                                                                         row_end, ix.img8_U, ix.d_img8, ix.d_img8_meta);
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
+int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
+    if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
+    ImgArgs im;
+    im.row_meta = ix.d_img8_meta;
+    im.q8 = ws.d_q8;
+    im.q_meta = ws.d_q8_meta;
+    im.pend = PendDev{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap};
+    im.dim_pad8 = ix.dim_pad8;
+    PKV_CUDA(cudaMemsetAsync(ws.d_pend_cnt, 0, sizeof(uint32_t) * a.nq, s));
+    img8_prep_queries_kernel<<<(a.nq + 7) / 8, 256, 0, s>>>((const float *)a.queries, a.nq, ix.dim, ix.dim_pad, ix.dim_pad8,
+                                                            a.q_mag_f, ws.d_q8, ws.d_q8_meta);
+    PKV_CUDA(cudaGetLastError());
+    *launches += 1;
+    CUtensorMap m64, m128;
+    PKV_TRY(make_tmap_bytes(&m64, ix.d_img8, (uint64_t)ix.dim_pad8, (uint64_t)ix.sealed_rows, (uint64_t)ix.dim_pad8, 64));
+    PKV_TRY(make_tmap_bytes(&m128, ix.d_img8, (uint64_t)ix.dim_pad8, (uint64_t)ix.sealed_rows, (uint64_t)ix.dim_pad8, 128));
+    const int kchunks = ix.dim_pad8 / CHUNK_BYTES;
+    switch (a.metric) {
+        case PKV_COSINE: PKV_TRY(launch_img8_metric<PKV_COSINE>(ix, a, im, m64, m128, kchunks, s, launches)); break;
+        case PKV_L2: PKV_TRY(launch_img8_metric<PKV_L2>(ix, a, im, m64, m128, kchunks, s, launches)); break;
+        default: PKV_TRY(launch_img8_metric<PKV_DOT>(ix, a, im, m64, m128, kchunks, s, launches)); break;
+    }
+    PKV_TRY(launch_rescore(ix, a, im.pend, ws.d_status, s));
+    *launches += 1;
+    return PKV_OK;
+}
+
+}  // namespace pkv

@@ -55,12 +55,6 @@ struct FShared {
     alignas(16) float qw[NQ];
 };
 
-struct PendDev {
-    uint32_t *rows;  // [nq][cap] rows awaiting exact re-scoring
-    uint32_t *cnt;   // [nq]
-    uint32_t cap;
-};
-
 struct FloatScan {
     const float *q_scale;  // [nq] accumulator -> true dot factor c_q; NULL = 1 (tf32)
     float eps;             // |dot~ - dot| <= eps |a||q|
@@ -587,21 +581,7 @@ int launch_metric(const Index &ix, const ScanArgs &a, const PendDev &pend, const
             q0 += 128;
         }
     }
-    const size_t smem = (size_t)a.dim_pad * 4;
-    int ry = (4 * ix.sm_count + a.nq - 1) / a.nq;  // ~4 CTAs per SM in total
-    if (ry < 1) ry = 1;
-    if (ry > 64) ry = 64;
-    const dim3 grid((unsigned)a.nq, (unsigned)ry);
-    if (ix.dtype == PKV_F16) {
-        auto rk = rescore_kernel<METRIC, true>;
-        PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rk<<<grid, 256, smem, s>>>(a, pend, status);
-    } else {
-        auto rk = rescore_kernel<METRIC, false>;
-        PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rk<<<grid, 256, smem, s>>>(a, pend, status);
-    }
-    PKV_CUDA(cudaGetLastError());
+    PKV_TRY(launch_rescore(ix, a, pend, status, s));
     *launches += 1;
     return PKV_OK;
 }
@@ -667,6 +647,33 @@ __global__ void shadow_convert_kernel(const float *rows, int64_t pitch_f, int di
 
 }  // namespace
 
+// Exact re-scoring of everything the filter kernels parked in `pend` (one launch for all queries).
+int launch_rescore(const Index &ix, const ScanArgs &a, const PendDev &pend, SearchStatus *status, cudaStream_t s) {
+    const size_t smem = (size_t)a.dim_pad * 4;
+    int ry = (4 * ix.sm_count + a.nq - 1) / a.nq;  // ~4 CTAs per SM in total
+    if (ry < 1) ry = 1;
+    if (ry > 64) ry = 64;
+    const dim3 grid((unsigned)a.nq, (unsigned)ry);
+#define PKV_RESCORE(M)                                                                                   \
+    do {                                                                                                 \
+        if (ix.dtype == PKV_F16) {                                                                       \
+            auto rk = rescore_kernel<M, true>;                                                           \
+            PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            rk<<<grid, 256, smem, s>>>(a, pend, status);                                                 \
+        } else {                                                                                         \
+            auto rk = rescore_kernel<M, false>;                                                          \
+            PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            rk<<<grid, 256, smem, s>>>(a, pend, status);                                                 \
+        }                                                                                                \
+    } while (0)
+    if (a.metric == PKV_COSINE) PKV_RESCORE(PKV_COSINE);
+    else if (a.metric == PKV_L2) PKV_RESCORE(PKV_L2);
+    else PKV_RESCORE(PKV_DOT);
+#undef PKV_RESCORE
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
 // TF32 keeps 10 explicit mantissa bits; whether the tensor core truncates or rounds the f32
 // operands, each is off by < 2^-10 relative, a product by < 2^-9, so
 // |dot~ - dot| <= 2^-9 * sum|a_i q_i| <= 2^-9 |a||q| (Cauchy-Schwarz); f32 accumulation adds ~1e-6.
@@ -679,31 +686,46 @@ static constexpr float F16_SHADOW_EPS = 1.25e-3f;
 // true f16 index: operands are exact, products are exact in f32, only the accumulation rounds
 static constexpr float F16_EXACT_EPS = 2.0e-4f;
 
+// which operand the filter scans: 2 int8 image, 1 fp16 image, 0 the rows themselves (tf32 / f16)
+static int image_choice(const Index &ix, int nq) {
+    const int want = ix.opt.use_shadow;
+    const bool f16_img = ix.dtype == PKV_F32 && ix.d_shadow && ix.shadow_scale != 0.f;
+    // best available: the int8 image halves the bytes of a pass but its error band passes ~5x more rows to the
+    // re-scorer than the fp16 image; past img8_max_queries per batch the fp16 image (if built) is the faster filter
+    if (want < 0 && img8_usable(ix) && f16_img && nq > ix.opt.img8_max_queries) return 1;
+    if ((want == 2 || want < 0) && img8_usable(ix)) return 2;
+    if ((want == 1 || want < 0 || want == 2) && ix.dtype == PKV_F32 && ix.d_shadow && ix.shadow_scale != 0.f) return 1;
+    return 0;
+}
+static bool use_shadow(const Index &ix, int nq) { return image_choice(ix, nq) == 1; }
+
 bool scan_tc_f32_supported(const Index &ix, int nq) {
     if (ix.opt.force_simt) return false;
     // with the fp16 image the tensor-core kernel reads half the bytes of the FFMA kernel, so it
     // wins from the very first query; the tf32 path reads the f32 rows and only pays off once the
     // FFMA kernel would need a second pass over the corpus
-    if (ix.dtype == PKV_F32) return (ix.d_shadow && ix.opt.use_shadow) ? nq >= ix.opt.tc_min_queries_img
-                                                                       : nq >= ix.opt.tc_min_queries_f32;
-    if (ix.dtype == PKV_F16) return nq >= ix.opt.tc_min_queries_f32;
+    if (image_choice(ix, nq) != 0) return nq >= ix.opt.tc_min_queries_img;
+    if (ix.dtype == PKV_F32 || ix.dtype == PKV_F16) return nq >= ix.opt.tc_min_queries_f32;
     return false;
 }
 
-static bool use_shadow(const Index &ix) { return ix.dtype == PKV_F32 && ix.d_shadow && ix.opt.use_shadow; }
 
-static float float_eps(const Index &ix) {
+static float float_eps(const Index &ix, int nq) {
+    if (image_choice(ix, nq) == 2) return 0.f;  // the int8-image kernel applies its own per-pair bound
     if (ix.dtype == PKV_F16) return F16_EXACT_EPS;
-    return use_shadow(ix) ? F16_SHADOW_EPS : TF32_EPS;
+    return use_shadow(ix, nq) ? F16_SHADOW_EPS : TF32_EPS;
 }
 
-FilterSpec filter_spec_tc_f32(const Index &ix, int metric) {
+FilterSpec filter_spec_tc_f32(const Index &ix, int metric, int nq) {
     FilterSpec fs = filter_spec_simt(PKV_F32, metric);
-    if (metric == PKV_COSINE) fs.abs = float_eps(ix);  // in units of dot/|a|: scaled by |q| in filter_threshold
+    if (metric == PKV_COSINE) fs.abs = float_eps(ix, nq);  // in units of dot/|a|: scaled by |q| in filter_threshold
     return fs;  // L2 / DOT apply the per-row bound inside the kernel
 }
 
-int scan_tc_f32_kind(const Index &ix) { return ix.dtype == PKV_F16 ? 6 : (use_shadow(ix) ? 7 : 4); }
+int scan_tc_f32_kind(const Index &ix, int nq) {
+    if (image_choice(ix, nq) == 2) return 8;
+    return ix.dtype == PKV_F16 ? 6 : (use_shadow(ix, nq) ? 7 : 4);
+}
 
 int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) {
     if (row_end <= row_begin) return PKV_OK;
@@ -718,10 +740,11 @@ int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) 
 
 int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
     if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
-    PendDev pend{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.cap};
+    if (image_choice(ix, a.nq) == 2) return launch_scan_img8(ix, a, ws, s, launches);
+    PendDev pend{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap};
     PKV_CUDA(cudaMemsetAsync(ws.d_pend_cnt, 0, sizeof(uint32_t) * a.nq, s));
     FloatScan fsn;
-    fsn.eps = float_eps(ix);
+    fsn.eps = float_eps(ix, a.nq);
     fsn.prefetch_tiles = ix.opt.tc_prefetch_tiles;
     fsn.q_scale = nullptr;
     fsn.tiny_mag = 0.f;
@@ -732,7 +755,7 @@ int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaSt
     uint64_t qrows = ((uint64_t)a.nq + 127) / 128 * 128;
     if (qrows > (uint64_t)ws.nq_cap) qrows = (uint64_t)ws.nq_cap;
     if (qrows < (uint64_t)a.nq) qrows = (uint64_t)a.nq;
-    const bool shadow = use_shadow(ix);
+    const bool shadow = use_shadow(ix, a.nq);
     if (ix.dtype == PKV_F32 && !shadow) {
         PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.pitch, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, TILE_M));
         PKV_TRY(make_tmap_bytes(&mq128, a.queries, (uint64_t)ix.pitch, qrows, (uint64_t)ix.pitch, 128));

@@ -60,23 +60,6 @@ struct TsShared {
     uint32_t hold_col[EPI_WARPS][HOLD_CAP];
 };
 
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// D[tmem] (+)= A[tmem] * B[smem]^T, M = 256 across the CTA pair
-__device__ __forceinline__ void mma_i8_ts_cta2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 // Exact filter, exact key, candidate push for one pre-filter survivor (col = query within the CTA).
 template <int METRIC>
 __device__ __noinline__ void consider_ts(const ScanArgs &a, int qbase, int col, int d, uint32_t row, const TsShared *sh) {
@@ -179,9 +162,9 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32));
             const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32 + 16));
             const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            tmem_st_32x8(lane_addr + (uint32_t)c8 * 8, v);
+            tc::tmem_st_32x8(lane_addr + (uint32_t)c8 * 8, v);
         }
-        tmem_st_wait();
+        tc::tmem_st_wait();
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -238,7 +221,7 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
                             if (j < n) {
 #pragma unroll
                                 for (int k = 0; k < CHUNK_BYTES / 32; ++k)
-                                    mma_i8_ts_cta2(d_tmem, a_tmem + j * (CHUNK_BYTES / 4) + k * 8,
+                                    tc::mma_i8_ts_cta2(d_tmem, a_tmem + j * (CHUNK_BYTES / 4) + k * 8,
                                                    b_desc + (uint64_t)(j * (BOX_BYTES / 16) + k * 2), idesc, (kc | j | k) != 0);
                             }
                         }

@@ -56,8 +56,12 @@ def assert_close_topk(got, want, corpus, queries, metric, rtol=F32_RTOL, atol=1e
         assert np.array_equal(nan_g, nan_o), f"query {q}: NaN placement differs"
         ok = ~nan_o
         tol = _tol(do[ok], metric, rtol, atol)
-        assert np.all(np.abs(dg[ok] - do[ok]) <= tol), (
-            f"query {q}: max rel err {np.max(np.abs(dg[ok]-do[ok])/np.maximum(np.abs(do[ok]),1e-30))}")
+        with np.errstate(invalid="ignore"):
+            close = (np.abs(dg[ok] - do[ok]) <= tol) | (dg[ok] == do[ok])   # equal infinities are equal
+        if not np.all(close):
+            i = int(np.argmin(close))
+            raise AssertionError(f"query {q}: position {i} of the valid entries: got d={dg[ok][i]!r} (id {ids_g[q, :m][ok][i]}) "
+                                 f"want d={do[ok][i]!r} (row {rows_o[q, :m][ok][i]}); {int((~close).sum())} entries differ")
         assert np.all(ids_g[q, m:] == -1)
         if np.array_equal(ids_g[q, :m], rows_o[q, :m]):
             continue
@@ -65,7 +69,9 @@ def assert_close_topk(got, want, corpus, queries, metric, rtol=F32_RTOL, atol=1e
         # and rows only one side returned must sit within rtol of the k-th distance
         d_rows = orc.distances(corpus[ids_g[q, :m]], queries[q], metric)
         fin = ~np.isnan(d_rows)
-        assert np.all(np.abs(d_rows[fin] - dg[fin]) <= _tol(d_rows[fin], metric, rtol, atol)), f"query {q}: row distance mismatch"
+        with np.errstate(invalid="ignore"):
+            same = (np.abs(d_rows[fin] - dg[fin]) <= _tol(d_rows[fin], metric, rtol, atol)) | (d_rows[fin] == dg[fin])
+        assert np.all(same), f"query {q}: row distance mismatch"
         kth = do[ok][-1] if ok.any() else 0.0
         only_g = np.setdiff1d(ids_g[q, :m], rows_o[q, :m])
         only_o = np.setdiff1d(rows_o[q, :m], ids_g[q, :m])

@@ -1,5 +1,7 @@
-"""f32 tensor-core path (tf32 filter + exact FFMA re-scoring): scores within 1e-5 relative of the
-oracle, and the same answer as the CUDA-core kernel (same summation order in the re-scoring)."""
+"""Floating-point tensor-core paths (reduced-precision tcgen05 filter + exact FFMA re-scoring): scores within
+1e-5 relative of the oracle, and the same answer as the CUDA-core kernel (same summation order in the
+re-scoring).  Filter operands (`use_shadow`): 2 = int8 image (per-row scales, kind::i8, queries in TMEM),
+1 = fp16 image (kind::f16), 0 = the f32 rows themselves (kind::tf32)."""
 import numpy as np
 import pytest
 
@@ -11,14 +13,18 @@ pytestmark = pytest.mark.gpu
 METRICS = [pk.L2, pk.COSINE, pk.DOT]
 
 
+KIND = {2: 8, 1: 7, 0: 4}   # counters().last_scan_kind per filter operand
+
+
 def _index(x):
     ix = pk.VectorIndex(x.shape[1], pk.F32)
+    ix.set_option("image_mask", 3)   # build both images so that every filter can be selected
     ix.append(x)
     ix.seal()
     return ix
 
 
-@pytest.mark.parametrize("shadow", [1, 0])
+@pytest.mark.parametrize("shadow", [2, 1, 0])
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("nq", [17, 128, 300])
 def test_tc_f32_matches_oracle_and_simt(metric, nq, shadow):
@@ -26,8 +32,7 @@ def test_tc_f32_matches_oracle_and_simt(metric, nq, shadow):
     with _index(x) as ix:
         ix.set_option("use_shadow", shadow)
         got = ix.search(q, 100, metric)
-        # 7 = fp16-image filter (kind::f16 on the scaled shadow), 4 = tf32 filter on the f32 rows
-        assert ix.counters().last_scan_kind == (7 if shadow else 4), "tensor-core kernel did not run"
+        assert ix.counters().last_scan_kind == KIND[shadow], "tensor-core kernel did not run"
         ix.set_option("force_simt", 1)
         simt = ix.search(q, 100, metric)
         assert ix.counters().last_scan_kind == 1
@@ -47,10 +52,12 @@ def test_tc_f32_dims_unnormalised(dim):
     q = orc.synthetic(40, dim, 212, normalise=False)
     q[3] *= 100.0
     with _index(x) as ix:
-        for metric in METRICS:
-            got = ix.search(q, 33, metric)
-            assert ix.counters().last_scan_kind in (4, 7)
-            assert_close_topk(got, orc.topk(x, q, metric, 33, threads=8), x, q, metric)
+        for shadow in (2, 1):
+            ix.set_option("use_shadow", shadow)
+            for metric in METRICS:
+                got = ix.search(q, 33, metric)
+                assert ix.counters().last_scan_kind in (4, 7, 8)
+                assert_close_topk(got, orc.topk(x, q, metric, 33, threads=8), x, q, metric)
 
 
 def test_tc_f32_near_duplicates_and_bitmap():
@@ -63,8 +70,10 @@ def test_tc_f32_near_duplicates_and_bitmap():
     words = (len(x) + 63) // 64
     bm = np.packbits(rng.random(words * 64) < 0.5, bitorder="little").view(np.uint64)
     with _index(x) as ix:
-        for metric in (pk.COSINE, pk.L2):
-            assert_close_topk(ix.search(q, 200, metric), orc.topk(x, q, metric, 200, threads=8), x, q, metric)
+        for shadow in (1, 2):
+            ix.set_option("use_shadow", shadow)
+            for metric in (pk.COSINE, pk.L2):
+                assert_close_topk(ix.search(q, 200, metric), orc.topk(x, q, metric, 200, threads=8), x, q, metric)
         got = ix.search(q, 50, pk.COSINE, bitmap=bm)
         want = orc.topk(x, q, orc.COSINE, 50, bitmap=bm, threads=8)
         assert np.array_equal(got[2], want[2])
@@ -83,10 +92,12 @@ def test_tc_shadow_tiny_and_huge_rows():
     q = orc.synthetic(32, 128, 232)
     q[:8] = x[:8] / np.linalg.norm(x[:8], axis=1, keepdims=True)   # queries parallel to rows of every scale
     with _index(x) as ix:
-        for metric in (pk.COSINE, pk.DOT, pk.L2):
-            got = ix.search(q, 25, metric)
-            assert ix.counters().last_scan_kind == 7
-            assert_close_topk(got, orc.topk(x, q, metric, 25, threads=8), x, q, metric)
+        for shadow in (1, 2):
+            ix.set_option("use_shadow", shadow)
+            for metric in (pk.COSINE, pk.DOT, pk.L2):
+                got = ix.search(q, 25, metric)
+                assert ix.counters().last_scan_kind == KIND[shadow]
+                assert_close_topk(got, orc.topk(x, q, metric, 25, threads=8), x, q, metric)
         for i in range(8):
             assert ix.search(q[i:i + 1], 1, pk.COSINE)[0][0][0] == i or True
 
@@ -99,8 +110,14 @@ def test_tc_f16_index():
     ix.seal()
     with ix:
         for metric in METRICS:
+            img = ix.search(q, 100, metric)           # int8 image of the f16 rows
+            assert ix.counters().last_scan_kind == 8
+            assert_close_topk(img, orc.topk(x, q, metric, 100, threads=8), x, q, metric)
+            ix.set_option("use_shadow", 0)            # kind::f16 on the rows themselves
             got = ix.search(q, 100, metric)
+            ix.set_option("use_shadow", -1)
             assert ix.counters().last_scan_kind == 6
+            assert np.array_equal(got[0], img[0]) and np.array_equal(got[1].view(np.uint32), img[1].view(np.uint32))
             assert_close_topk(got, orc.topk(x, q, metric, 100, threads=8), x, q, metric)
             ix.set_option("force_simt", 1)
             simt = ix.search(q, 100, metric)
@@ -124,7 +141,7 @@ def test_shadow_survives_incremental_appends_with_growing_range():
             assert_close_topk(ix.search(q, 10, metric), orc.topk(x, q, metric, 10, threads=4), x, q, metric)
 
 
-@pytest.mark.parametrize("shadow", [1, 0])
+@pytest.mark.parametrize("shadow", [2, 1, 0])
 def test_tc_float_cta_pair_matches_single_cta(shadow):
     x, q = orc.synthetic(70007, 512, 261), orc.synthetic(256, 512, 262)
     with _index(x) as ix:
@@ -136,3 +153,52 @@ def test_tc_float_cta_pair_matches_single_cta(shadow):
             ix.set_option("tc_cta2", 1)
             assert np.array_equal(pair[0], single[0]) and np.array_equal(pair[1].view(np.uint32), single[1].view(np.uint32))
             assert_close_topk(pair, orc.topk(x, q, metric, 50, threads=16), x, q, metric)
+
+
+def test_img8_non_finite_rows_and_queries():
+    # NaN / inf components cannot be quantised: such rows (and queries) bypass the filter and are re-scored
+    x = orc.synthetic(9000, 256, 271)
+    x[5, 3] = np.inf
+    x[6, 7] = np.nan
+    x[7] = 0.0
+    x[8] *= np.float32(1e-30)
+    x[9] *= np.float32(1e30)
+    q = orc.synthetic(130, 256, 272)
+    q[2] *= np.float32(1e-20)
+    with _index(x) as ix:
+        for shadow in (1, 2):
+            ix.set_option("use_shadow", shadow)
+            for metric in METRICS:
+                got = ix.search(q, 20, metric)
+                assert ix.counters().last_scan_kind == KIND[shadow]
+                # the 1e30-scaled row has a dot product 1000x smaller than its terms: summation order alone moves
+                # it by > 1e-5 relative, and its size puts it in every DOT top-k
+                rtol = 1e-3 if metric == pk.DOT else 1e-5
+                assert_close_topk(got, orc.topk(x, q, metric, 20, threads=8), x, q, metric, rtol=rtol)
+
+
+@pytest.mark.parametrize("nq", [1, 64, 129, 512, 1024])
+def test_img8_batches_and_k(nq):
+    x, q = orc.synthetic(50021, 768, 281), orc.synthetic(nq, 768, 282)
+    with _index(x) as ix:
+        got = ix.search(q, 100, pk.COSINE)
+        assert ix.counters().last_scan_kind == 8
+        assert_close_topk(got, orc.topk(x, q, orc.COSINE, 100, threads=16), x, q, orc.COSINE)
+        if nq <= 64:
+            big = ix.search(q, 1000, pk.L2)   # deep k: the filter passes several rows per true candidate
+            assert_close_topk(big, orc.topk(x, q, orc.L2, 1000, threads=16), x, q, orc.L2)
+
+
+def test_img8_incremental_appends():
+    x1 = orc.synthetic(5000, 64, 291)
+    x2 = orc.synthetic(3000, 64, 292) * np.float32(1000.0)
+    q = orc.synthetic(20, 64, 293)
+    ix = pk.VectorIndex(64, pk.F32)
+    with ix:
+        ix.append(x1); ix.seal()
+        assert_close_topk(ix.search(q, 10, pk.COSINE), orc.topk(x1, q, orc.COSINE, 10), x1, q, orc.COSINE)
+        assert ix.counters().last_scan_kind == 8
+        ix.append(x2); ix.seal()
+        x = np.concatenate([x1, x2])
+        for metric in METRICS:
+            assert_close_topk(ix.search(q, 10, metric), orc.topk(x, q, metric, 10, threads=4), x, q, metric)
