@@ -188,6 +188,7 @@ struct Options {
     int use_shadow = -1;             // which image the tensor-core filter scans: -1 best available, 0 none (tf32 on
                                      // the f32 rows), 1 fp16 image, 2 int8 image
     int img8_max_queries = 1 << 30;  // best-available choice: batches above this use the fp16 image when both exist
+    int img8_peak_sigma_x10 = 30;    // int8 image: rows up to mean + this/10 sigma of peakiness quantise without saturation
     int image_mask = 2;              // images built at seal for f32/f16 indexes: bit 0 fp16 (f32 only), bit 1 int8
     int tc_prefetch_tiles = 0;       // L2 prefetch distance of the TMA producer, in tiles per CTA
     int tc_cta2 = 1;                 // use the 2-CTA (cta_group::2) kernels when the batch is large enough

@@ -635,7 +635,7 @@ int build_img8(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) {
             const double mean = h[0] / h[2];
             double var = h[1] / h[2] - mean * mean;
             if (var < 0) var = 0;
-            p_ref = mean + 1.3 * sqrt(var);
+            p_ref = mean + 0.1 * ix.opt.img8_peak_sigma_x10 * sqrt(var);
             if (p_ref > 1.0) p_ref = 1.0;
             if (p_ref < 1e-3) p_ref = 1e-3;
         }
