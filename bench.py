@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--metric", default="cosine", choices=["cosine", "l2", "dot"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--bitmap-density", type=float, default=0.0,
+                    help="BASELINE config 5: AND the scan with a tag-filter row bitmap of this density (shared by the batch)")
     ap.add_argument("--force-simt", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="index option name=value (tuning experiments)")
     return ap.parse_args()
@@ -53,7 +55,8 @@ def parse_args():
 
 def workload_name(a) -> str:
     n = f"{a.rows // 1_000_000}M" if a.rows % 1_000_000 == 0 else str(a.rows)
-    return f"{n}x{a.dim} {a.dtype} {a.metric} top-{a.k}, batch={a.batch} queries"
+    tag = f" AND tag bitmap (density {a.bitmap_density:g})" if a.bitmap_density > 0 else ""
+    return f"{n}x{a.dim} {a.dtype} {a.metric} top-{a.k}, batch={a.batch} queries{tag}"
 
 
 # ------------------------------------------------------------------ synthetic data
@@ -289,9 +292,18 @@ def main():
         g_packed = torch.empty((world, a.batch, a.k, 3), dtype=torch.int32, device=dev)
 
     merge_launches = [0]
+    # config 5: membership bits over this shard's rows (Bernoulli(p), seed 0x5EED+2 over GLOBAL rows: SURVEY 8d),
+    # packed LSB-first into u64 words; the same bitmap for every query of the batch (context of an AND filter)
+    bm_dev = bm_host = None
+    if a.bitmap_density > 0:
+        member = np.random.default_rng(CORPUS_SEED + 2).random(a.rows) < a.bitmap_density
+        local = np.zeros(((r1 - r0 + 63) // 64) * 64, dtype=bool)
+        local[: r1 - r0] = member[r0:r1]
+        bm_host = np.packbits(local, bitorder="little").view(np.uint64).copy()
+        bm_dev = torch.from_numpy(bm_host.view(np.int64)).to(dev)
 
     def step_device(q):
-        ids, dst, cnt = ix.search(q, a.k, metric_code, out=out_dev)
+        ids, dst, cnt = ix.search(q, a.k, metric_code, out=out_dev, bitmap=bm_dev)
         if world == 1:
             return ids, dst, cnt
         # ONE all-gather of the per-shard candidates (ids and distances packed side by side)
@@ -336,7 +348,7 @@ def main():
     value = a.batch / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with HOST buffers: `e2e`
-    h2d = a.batch * a.dim * elem
+    h2d = a.batch * a.dim * elem + (bm_host.nbytes if bm_host is not None else 0)
     d2h = a.batch * a.k * 12 + a.batch * 4
     out_host = (np.empty((a.batch, a.k), np.int64), np.empty((a.batch, a.k), np.float32), np.empty(a.batch, np.int32))
     out_pinned = [torch.from_numpy(o).pin_memory() for o in out_host]
@@ -345,7 +357,7 @@ def main():
     def step_e2e(qp):
         if world == 1:
             # the C-ABI host call: H2D of the queries, scan, D2H of ids/dist/counts, all inside
-            return ix.search(qp.numpy(), a.k, metric_code, out=out_pinned_np)
+            return ix.search(qp.numpy(), a.k, metric_code, out=out_pinned_np, bitmap=bm_host)
         q = qp.to(dev, non_blocking=True)
         ids, dst, cnt = step_device(q)
         return ids.cpu(), dst.cpu(), cnt.cpu()
@@ -459,7 +471,7 @@ def main():
     }
 
     # ---- CPU baseline on a bounded sample of the same corpus + parity of the GPU path on that sample
-    if not a.no_cpu and sample_host:
+    if not a.no_cpu and sample_host and a.bitmap_density == 0:
         from oracle import oracle as orc
 
         orc.build()

@@ -199,7 +199,8 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
     }
     if (timed) PKV_CUDA(cudaEventRecord(ev_begin, r.s));
     int n = 0;
-    PKV_TRY(launch_reset_status(r.ws, r.s));
+    // per-chunk status (max_raw_cnt / any_overflow / min_filled) is only read after a synced chunk
+    if (sync) PKV_TRY(launch_reset_status(r.ws, r.s));
     // While some query has no threshold yet every pair is a candidate: that is dense work with one
     // push per pair, which the CUDA-core kernel does far more cheaply than the tensor-core
     // kernels' survivor path (built for rare survivors).
@@ -214,7 +215,7 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
     r.scan_launches += n;
     if (timed) PKV_CUDA(cudaEventRecord(ev_end, r.s));
     PKV_TRY(launch_select(r.ix, r.ws, r.nq, r.k, r.args.metric, r.fs, r.s));
-    r.launches += 2;
+    r.launches += sync ? 2 : 1;
     if (!sync) {
         r.unsynced++;
         return PKV_OK;
@@ -263,6 +264,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     const int64_t N = ix.sealed_rows;
     const int k = p.k;
     PKV_TRY(launch_prep_queries(ix, ws, d_qraw, nq, p.query_dtype, s));
+    ws.q8_ready = false;
     PKV_TRY(launch_reset_state(ws, nq, s));
     SearchRun r{ix, ws, s, ScanArgs{}, filter_spec_simt(ix.dtype, p.metric), nq, k, (int64_t)ws.cap - k};
     r.launches = 2;

@@ -160,6 +160,7 @@ struct Workspace {
     __half *d_q16 = nullptr;          // fp16-image path: scaled half queries [nq_cap][dim_pad_h]
     int8_t *d_q8 = nullptr;           // int8-image path: per-query quantised codes [nq_cap][dim_pad8]
     float4 *d_q8_meta = nullptr;      // {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2} per query
+    bool q8_ready = false;            // codes of the current batch are in d_q8
     float *d_q_scale = nullptr;       // accumulator -> dot factor per query
     SearchStatus *d_status = nullptr;
     SearchStatus *h_status = nullptr;  // pinned

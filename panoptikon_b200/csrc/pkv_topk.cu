@@ -69,10 +69,12 @@ __global__ void prep_queries_kernel(const void *qraw, int query_dtype, int index
     }
 }
 
-__global__ void reset_state_kernel(uint32_t *cnt, uint64_t *thr_key, float *thr_f, SearchStatus *st, int nq) {
+__global__ void reset_state_kernel(uint32_t *cnt, uint64_t *thr_key, float *thr_f, SearchStatus *st, int nq,
+                                   uint32_t *pend_cnt) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq) {
         cnt[i] = 0;
+        if (pend_cnt) pend_cnt[i] = 0;
         thr_key[i] = KEY_MAX;
         thr_f[i] = __int_as_float(0x7f800000);
     }
@@ -115,7 +117,7 @@ __device__ __forceinline__ float filter_threshold(FilterSpec fs, float d_k, floa
 // in cand[0..k) sorted ascending, and publishes the new exact and filter thresholds.
 __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *cnt, uint64_t *thr_key, float *thr_f,
                                                      const float *q_mag_f, SearchStatus *status, uint32_t cap, int k,
-                                                     FilterSpec fs) {
+                                                     FilterSpec fs, uint32_t *pend_cnt) {
     extern __shared__ uint64_t s_keys[];
     __shared__ uint64_t s_kth;
     __shared__ int s_m;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *c
     if (threadIdx.x == 0) {
         const uint32_t m = (uint32_t)s_m;
         cnt[q] = m;
+        if (pend_cnt) pend_cnt[q] = 0;  // the re-scorer has consumed this chunk's survivors
         thr_key[q] = s_kth;
         float tf = __int_as_float(0x7f800000);
         if (s_kth != KEY_MAX) tf = filter_threshold(fs, unordered_bits((uint32_t)(s_kth >> 32)), q_mag_f[q]);
@@ -399,7 +402,7 @@ int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int 
 
 int launch_reset_state(Workspace &ws, int nq, cudaStream_t s) {
     reset_state_kernel<<<(nq + 255) / 256 > 0 ? (nq + 255) / 256 : 1, 256, 0, s>>>(ws.d_cnt, ws.d_thr_key, ws.d_thr_f,
-                                                                                  ws.d_status, nq);
+                                                                                  ws.d_status, nq, ws.d_pend_cnt);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }
@@ -417,7 +420,7 @@ int launch_select(const Index &ix, Workspace &ws, int nq, int k, int metric, Fil
     const size_t smem = (size_t)ws.cap * sizeof(uint64_t);
     PKV_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_kernel<<<nq, 512, smem, s>>>(ws.d_cand, ws.d_cnt, ws.d_thr_key, ws.d_thr_f, ws.d_q_mag_f, ws.d_status,
-                                        (uint32_t)ws.cap, k, fs);
+                                        (uint32_t)ws.cap, k, fs, ws.d_pend_cnt);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }

@@ -202,3 +202,27 @@ def test_img8_incremental_appends():
         x = np.concatenate([x1, x2])
         for metric in METRICS:
             assert_close_topk(ix.search(q, 10, metric), orc.topk(x, q, metric, 10, threads=4), x, q, metric)
+
+
+def test_img8_peaky_and_sparse_rows():
+    # one-hot-like rows saturate the direction quantiser (their peakiness is far above the index's reference):
+    # their error term grows instead of their codes overflowing, and they are still ranked exactly
+    rng = np.random.default_rng(31)
+    x = orc.synthetic(12000, 384, 301)
+    hot = rng.integers(0, 384, size=3000)
+    x[:3000] *= np.float32(0.02)
+    x[np.arange(3000), hot] += rng.choice(np.float32([-1.0, 1.0]), size=3000)
+    x[3000:3100] = 0.0
+    x[3000:3100, 7] = np.float32(5.0)
+    q = orc.synthetic(140, 384, 302)
+    q[:20] = x[:20] * np.float32(3.0)          # queries parallel to peaky rows
+    q[20:30] = 0.0
+    q[20:30, 7] = 1.0                          # sparse queries
+    ix = pk.VectorIndex(384, pk.F32)
+    ix.append(x)
+    ix.seal()
+    with ix:
+        for metric in METRICS:
+            got = ix.search(q, 60, metric)
+            assert ix.counters().last_scan_kind == 8
+            assert_close_topk(got, orc.topk(x, q, metric, 60, threads=8), x, q, metric)
