@@ -423,6 +423,8 @@ def main():
                    }.get(kind, str(kind)),
         "algorithmic_bytes_per_row": row_bytes,
         "f32_equivalent_gbs": (shard_rows * a.dim * 4 / (scan_ms_step * 1e-3) / 1e9) if (kind in (7, 8) and a.dtype == "f32" and scan_ms_step > 0) else None,
+        # SURVEY 8(d) defines the fp32 roofline on N*D*4 bytes per pass: the same scan time against those bytes
+        "f32_hbm_roofline_frac": (shard_rows * a.dim * 4 / (scan_ms_step * 1e-3) / 1e9 / hbm_peak) if (a.dtype == "f32" and scan_ms_step > 0 and hbm_peak) else None,
         "launches_per_step": scan_launches, "kernel_ms_per_step": scan_ms_step,
         "algorithmic_bytes_per_step": alg_bytes, "algorithmic_ops_per_step": ops,
         "achieved_gbs": achieved_gbs, "achieved_tops": tput,

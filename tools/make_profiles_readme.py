@@ -22,7 +22,7 @@ for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*.json"))):
 out = ["# profiles/ — measured on B200 (gpurun), round 1", "",
        "Every line below is one `bench.py` JSON line committed in this directory (file name in the first column).",
        "`GB/s` = algorithmic bytes of the scanned image per step / CUDA-event time of the scan kernels;",
-       "`frac` = that / 6545.6 GB/s (measured copy bandwidth, MEASURED_PEAKS.json) or, for tensor-bound lines, TOP/s / peak.",
+       "`frac` = that / 6535 GB/s (measured copy bandwidth, MEASURED_PEAKS.json) or, for tensor-bound lines, TOP/s / peak.",
        "", "| file | workload | GPUs | queries/s | e2e queries/s | ms/step | scan kernel | scan ms | GB/s | TOP/s | bound | frac | CPU baseline q/s (cores) |",
        "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 for name, j, r, cb in rows:
