@@ -1049,6 +1049,7 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "tc_ts")) ix.opt.tc_ts = (int)value;
     else if (!strcmp(name, "ts_groups")) ix.opt.ts_groups = (int)value;
     else if (!strcmp(name, "ts_stages")) ix.opt.ts_stages = (int)value;
+    else if (!strcmp(name, "ts_acc_buffers")) ix.opt.ts_acc_buffers = (int)value;
     else if (!strcmp(name, "ts_chunks")) ix.opt.ts_chunks = (int)(value < 0 ? 0 : (value > 4 ? 4 : value));
     else if (!strcmp(name, "use_shadow")) ix.opt.use_shadow = (int)value;
     else if (!strcmp(name, "image_mask")) ix.opt.image_mask = (int)(value & 3);

@@ -35,14 +35,12 @@ namespace pkv {
 namespace {
 
 constexpr int QM_CTA = 128;
-constexpr int TILE_N = 128;
 constexpr int CHUNK_BYTES = 128;
 constexpr int MAX_STAGES = 26;
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int IMG_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COL0 = 256;
 constexpr int HOLD_CAP = 64;
 constexpr int HOLD_FLUSH = 32;
 constexpr float BOUND_CLAMP = 1.07e9f;
@@ -58,8 +56,8 @@ struct ImgArgs {
 struct ImgShared {
     uint64_t full[MAX_STAGES];
     uint64_t empty[MAX_STAGES];
-    uint64_t tmem_full[2];
-    uint64_t tmem_empty[2];
+    uint64_t tmem_full[3];
+    uint64_t tmem_empty[3];
     uint32_t tmem_base;
     uint32_t pad;
     uint32_t hold_cnt[EPI_WARPS];
@@ -158,11 +156,16 @@ __device__ __forceinline__ float warp_max_nn(float v) {
     return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
 
-template <int METRIC, int CPS, bool PAIR>
+// TN = rows per tile (MMA N), NBUF = accumulator buffers in TMEM (three hide the commit -> tcgen05.ld -> arrive ->
+// re-issue round trip of a buffer, see pkv_scan_ts.cu).
+template <int METRIC, int CPS, bool PAIR, int TN, int NBUF>
 __global__ void __launch_bounds__(IMG_THREADS, 1)
 scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a, const ImgArgs im, const int q0,
                  const int groups, const int kchunks, const int stages) {
-    constexpr int ROWS_CTA = PAIR ? 64 : 128;          // rows this CTA stages per tile
+    constexpr int TILE_N = TN;
+    constexpr int EPI_USED = (TN / 32) * 4;            // epilogue warps with work: 32 accumulator columns each
+    const uint32_t acc_col0 = (uint32_t)(im.dim_pad8 / 4 + 31) / 32 * 32;  // accumulators behind the query columns
+    constexpr int ROWS_CTA = PAIR ? TN / 2 : TN;       // rows this CTA stages per tile
     constexpr int BOX_BYTES = ROWS_CTA * CHUNK_BYTES;  // one TMA box
     constexpr int STAGE_BYTES = CPS * BOX_BYTES;
     constexpr int NCTA = PAIR ? 2 : 1;
@@ -186,9 +189,9 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             tc::mbar_init(&sh->full[s], 1);
             tc::mbar_init(&sh->empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             tc::mbar_init(&sh->tmem_full[b], 1);
-            tc::mbar_init(&sh->tmem_empty[b], NCTA * EPI_WARPS);
+            tc::mbar_init(&sh->tmem_empty[b], NCTA * EPI_USED);
         }
         for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
         tc::fence_barrier_init();
@@ -285,12 +288,11 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         if (rank == 0 && seq < nseq) {
             constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, NCTA * QM_CTA, TILE_N);
             const bool issuer = tc::elect_one();
-            uint32_t s = 0, ph = 0, t = 0;
-            for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
-                const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            uint32_t s = 0, ph = 0, buf = 0, bph = 0;
+            for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
                 tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
                 tc::fence_after_sync();
-                const uint32_t d_tmem = tmem_base + ACC_COL0 + buf * TILE_N;
+                const uint32_t d_tmem = tmem_base + acc_col0 + buf * TILE_N;
                 for (int kc = 0; kc < kchunks; kc += CPS) {
                     const int n = kchunks - kc < CPS ? kchunks - kc : CPS;
                     tc::mbar_wait(&sh->full[s], ph);
@@ -321,23 +323,22 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                     else tc::mma_commit(&sh->tmem_full[buf]);
                 }
                 __syncwarp();
+                if (++buf == NBUF) { buf = 0; bph ^= 1; }
             }
         }
-    } else if (seq < nseq) {
-        // ===================== epilogue: own 128 queries x the tile's 128 rows =====================
+    } else if (seq < nseq && warp - 2 < EPI_USED) {
+        // ===================== epilogue: own 128 queries x the tile's rows =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int col0 = (ew >> 2) * 32;       // accumulator columns = rows of the tile
         const int qcol = quarter * 32 + lane;  // this thread's query within the CTA
-        uint32_t t = 0;
+        uint32_t buf = 0, bph = 0;
         // lane j prefetches the figures of row col0 + j (the warp's 32 rows of the tile)
         uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
         bool row_ok = seq < ntiles && nrow < a.row_end;
         float4 m = row_ok ? __ldg(im.row_meta + nrow) : make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t empty0 = PAIR ? tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0) : tc::smem_u32(&sh->tmem_empty[0]);
-        const uint32_t empty1 = PAIR ? tc::mapa(tc::smem_u32(&sh->tmem_empty[1]), 0) : tc::smem_u32(&sh->tmem_empty[1]);
-        for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
-            const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+        for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
             // loosest figures over the warp's 32 rows (rows past the end must not loosen them)
             float x1, x2;
@@ -358,14 +359,15 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();
             uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ACC_COL0 + buf * TILE_N + col0, v);
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col0 + buf * TILE_N + col0, v);
             tc::tmem_ld_wait();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) {
-                if (PAIR) tc::mbar_arrive_cluster(buf ? empty1 : empty0);  // accumulator is in registers
+                if (PAIR) tc::mbar_arrive_cluster(empty0 + buf * 8u);  // accumulator is in registers
                 else tc::mbar_arrive(&sh->tmem_empty[buf]);
             }
+            if (++buf == NBUF) { buf = 0; bph ^= 1; }
             // sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once
             int any = 0;
 #pragma unroll
@@ -547,18 +549,20 @@ __global__ void __launch_bounds__(256) img8_prep_queries_kernel(const float *q, 
     }
 }
 
-template <int METRIC, int CPS, bool PAIR>
-int launch_img8(const Index &ix, const ScanArgs &a, const ImgArgs &im, const CUtensorMap &mrows, int q0, int groups,
-                int kchunks, cudaStream_t s) {
-    constexpr int STAGE_BYTES = CPS * (PAIR ? 64 : 128) * CHUNK_BYTES;
+template <int METRIC, int CPS, bool PAIR, int TN, int NBUF>
+int launch_img8(const Index &ix, const ScanArgs &a, const ImgArgs &im, int q0, int groups, int kchunks, cudaStream_t s) {
+    constexpr int ROWS_CTA = PAIR ? TN / 2 : TN;
+    constexpr int STAGE_BYTES = CPS * ROWS_CTA * CHUNK_BYTES;
+    CUtensorMap mrows;
+    PKV_TRY(make_tmap_bytes(&mrows, ix.d_img8, (uint64_t)ix.dim_pad8, (uint64_t)ix.sealed_rows, (uint64_t)ix.dim_pad8, ROWS_CTA));
     const size_t ctrl = sizeof(ImgShared);
     int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE_BYTES);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (ix.opt.ts_stages > 1 && ix.opt.ts_stages < stages) stages = ix.opt.ts_stages;
     const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + ctrl;
-    auto kernel = scan_img8_kernel<METRIC, CPS, PAIR>;
+    auto kernel = scan_img8_kernel<METRIC, CPS, PAIR, TN, NBUF>;
     PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t ntiles = (a.row_end - a.row_begin + TILE_N - 1) / TILE_N;
+    const uint32_t ntiles = (a.row_end - a.row_begin + TN - 1) / TN;
     uint32_t units = PAIR ? (uint32_t)ix.sm_count / 2 : (uint32_t)ix.sm_count;
     units = units / groups * groups;
     const uint32_t want = ntiles * (uint32_t)groups;
@@ -579,9 +583,19 @@ int launch_img8(const Index &ix, const ScanArgs &a, const ImgArgs &im, const CUt
     return PKV_OK;
 }
 
+// Tile shape by what TMEM has left behind the query columns (see pkv_scan_ts.cu)
+template <int METRIC, int CPS, bool PAIR>
+int launch_img8_shape(const Index &ix, const ScanArgs &a, const ImgArgs &im, int q0, int groups, int kchunks,
+                      cudaStream_t s) {
+    const int free_cols = TMEM_COLS - (ix.dim_pad8 / 4 + 31) / 32 * 32;
+    const int nbuf_opt = ix.opt.ts_acc_buffers;
+    if (nbuf_opt != 2 && free_cols >= 384) return launch_img8<METRIC, CPS, PAIR, 128, 3>(ix, a, im, q0, groups, kchunks, s);
+    if (nbuf_opt != 2 && free_cols >= 288) return launch_img8<METRIC, CPS, PAIR, 96, 3>(ix, a, im, q0, groups, kchunks, s);
+    return launch_img8<METRIC, CPS, PAIR, 128, 2>(ix, a, im, q0, groups, kchunks, s);
+}
+
 template <int METRIC>
-int launch_img8_metric(const Index &ix, const ScanArgs &a, const ImgArgs &im, const CUtensorMap &m64,
-                       const CUtensorMap &m128, int kchunks, cudaStream_t s, int *launches) {
+int launch_img8_metric(const Index &ix, const ScanArgs &a, const ImgArgs &im, int kchunks, cudaStream_t s, int *launches) {
     const int cps = (kchunks % 3 == 0) ? 3 : 2;
     const bool pairs_ok = (ix.sm_count % 2) == 0 && ix.opt.tc_cta2;
     int gmax = ix.opt.ts_groups;
@@ -593,12 +607,12 @@ int launch_img8_metric(const Index &ix, const ScanArgs &a, const ImgArgs &im, co
         if (left > QM_CTA && pairs_ok) {
             int groups = (left + 2 * QM_CTA - 1) / (2 * QM_CTA);
             if (groups > gmax) groups = gmax;
-            if (cps == 3) PKV_TRY((launch_img8<METRIC, 3, true>(ix, a, im, m64, q0, groups, kchunks, s)));
-            else PKV_TRY((launch_img8<METRIC, 2, true>(ix, a, im, m64, q0, groups, kchunks, s)));
+            if (cps == 3) PKV_TRY((launch_img8_shape<METRIC, 3, true>(ix, a, im, q0, groups, kchunks, s)));
+            else PKV_TRY((launch_img8_shape<METRIC, 2, true>(ix, a, im, q0, groups, kchunks, s)));
             q0 += groups * 2 * QM_CTA;
         } else {
-            if (cps == 3) PKV_TRY((launch_img8<METRIC, 3, false>(ix, a, im, m128, q0, 1, kchunks, s)));
-            else PKV_TRY((launch_img8<METRIC, 2, false>(ix, a, im, m128, q0, 1, kchunks, s)));
+            if (cps == 3) PKV_TRY((launch_img8_shape<METRIC, 3, false>(ix, a, im, q0, 1, kchunks, s)));
+            else PKV_TRY((launch_img8_shape<METRIC, 2, false>(ix, a, im, q0, 1, kchunks, s)));
             q0 += QM_CTA;
         }
     }
@@ -668,14 +682,11 @@ int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStre
         *launches += 1;
         ws.q8_ready = true;
     }
-    CUtensorMap m64, m128;
-    PKV_TRY(make_tmap_bytes(&m64, ix.d_img8, (uint64_t)ix.dim_pad8, (uint64_t)ix.sealed_rows, (uint64_t)ix.dim_pad8, 64));
-    PKV_TRY(make_tmap_bytes(&m128, ix.d_img8, (uint64_t)ix.dim_pad8, (uint64_t)ix.sealed_rows, (uint64_t)ix.dim_pad8, 128));
     const int kchunks = ix.dim_pad8 / CHUNK_BYTES;
     switch (a.metric) {
-        case PKV_COSINE: PKV_TRY(launch_img8_metric<PKV_COSINE>(ix, a, im, m64, m128, kchunks, s, launches)); break;
-        case PKV_L2: PKV_TRY(launch_img8_metric<PKV_L2>(ix, a, im, m64, m128, kchunks, s, launches)); break;
-        default: PKV_TRY(launch_img8_metric<PKV_DOT>(ix, a, im, m64, m128, kchunks, s, launches)); break;
+        case PKV_COSINE: PKV_TRY(launch_img8_metric<PKV_COSINE>(ix, a, im, kchunks, s, launches)); break;
+        case PKV_L2: PKV_TRY(launch_img8_metric<PKV_L2>(ix, a, im, kchunks, s, launches)); break;
+        default: PKV_TRY(launch_img8_metric<PKV_DOT>(ix, a, im, kchunks, s, launches)); break;
     }
     PKV_TRY(launch_rescore(ix, a, im.pend, ws.d_status, s));
     *launches += 1;

@@ -32,24 +32,20 @@ namespace {
 
 constexpr int QM_CTA = 128;     // queries per CTA (TMEM lanes)
 constexpr int QM = 256;         // queries per pair (MMA M)
-constexpr int TILE_N = 128;     // corpus rows per tile (MMA N)
-constexpr int ROWS_CTA = 64;    // rows staged by each CTA per tile
 constexpr int CHUNK_BYTES = 128;
-constexpr int BOX_BYTES = ROWS_CTA * CHUNK_BYTES;  // one TMA box: 64 rows x 128 B = 8 KiB
 constexpr int MAX_STAGES = 26;
 constexpr int EPI_WARPS = 16;   // lane quarter = warp & 3, 32 accumulator columns each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TS_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COL0 = 256;   // accumulators behind the query columns (dim_pad <= 1024)
 constexpr int HOLD_CAP = 64;
 constexpr int HOLD_FLUSH = 32;
 
 struct TsShared {
     uint64_t full[MAX_STAGES];
     uint64_t empty[MAX_STAGES];
-    uint64_t tmem_full[2];
-    uint64_t tmem_empty[2];
+    uint64_t tmem_full[3];
+    uint64_t tmem_empty[3];
     uint32_t tmem_base;
     uint32_t pad;
     uint32_t hold_cnt[EPI_WARPS];
@@ -99,10 +95,20 @@ __device__ __forceinline__ void flush_ts(const ScanArgs &a, int qbase, TsShared 
     __syncwarp();
 }
 
-template <int METRIC, int CPS>
+// TN = corpus rows per tile (MMA N), NBUF = accumulator buffers in TMEM behind the query columns.  The round trip
+// "MMAs of tile t done -> commit -> epilogue warps wake -> tcgen05.ld -> (remote) arrive -> issuing warp wakes ->
+// first MMA of the tile that reuses the buffer" costs ~1500-2000 clocks, about one 128-row tile of tensor work, so
+// with two buffers the pipe idled ~25-40 % of the time; three buffers hide it (96-row tiles when D > 512 leaves
+// only 320 TMEM columns).
+template <int METRIC, int CPS, int TN, int NBUF>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a, const int q0, const int groups,
                   const int kchunks, const int stages) {
+    constexpr int TILE_N = TN;
+    constexpr int ROWS_CTA = TN / 2;                   // rows staged by each CTA per tile
+    constexpr int BOX_BYTES = ROWS_CTA * CHUNK_BYTES;  // one TMA box
+    constexpr int EPI_USED = (TN / 32) * 4;            // epilogue warps with work: 32 accumulator columns each
+    const uint32_t acc_col0 = (uint32_t)(a.dim_pad / 4 + 31) / 32 * 32;  // accumulators behind the query columns
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -123,9 +129,9 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             tc::mbar_init(&sh->full[s], 1);
             tc::mbar_init(&sh->empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             tc::mbar_init(&sh->tmem_full[b], 1);
-            tc::mbar_init(&sh->tmem_empty[b], 2 * EPI_WARPS);
+            tc::mbar_init(&sh->tmem_empty[b], 2 * EPI_USED);
         }
         for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
         tc::fence_barrier_init();
@@ -203,12 +209,11 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
         if (rank == 0 && seq < nseq) {
             constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, QM, TILE_N);
             const bool issuer = tc::elect_one();
-            uint32_t s = 0, ph = 0, t = 0;
-            for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
-                const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            uint32_t s = 0, ph = 0, buf = 0, bph = 0;
+            for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
                 tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
                 tc::fence_after_sync();
-                const uint32_t d_tmem = tmem_base + ACC_COL0 + buf * TILE_N;
+                const uint32_t d_tmem = tmem_base + acc_col0 + buf * TILE_N;
                 for (int kc = 0; kc < kchunks; kc += CPS) {
                     const int n = kchunks - kc < CPS ? kchunks - kc : CPS;
                     tc::mbar_wait(&sh->full[s], ph);
@@ -232,22 +237,21 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
                 }
                 if (issuer) tc::mma_commit_cta2(&sh->tmem_full[buf]);
                 __syncwarp();
+                if (++buf == NBUF) { buf = 0; bph ^= 1; }
             }
         }
-    } else if (seq < nseq) {
-        // ===================== epilogue (both CTAs: own 128 queries x the tile's 128 rows) =====================
+    } else if (seq < nseq && warp - 2 < EPI_USED) {
+        // ===================== epilogue (both CTAs: own 128 queries x the tile's rows) =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int col0 = (ew >> 2) * 32;           // accumulator columns = rows of the tile
         const int qcol = quarter * 32 + lane;      // this thread's query within the CTA
-        uint32_t t = 0;
+        uint32_t buf = 0, bph = 0;
         // lane j prefetches the norm of row col0 + j (the warp's 32 rows of the tile)
         uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
         int am = (seq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
         const uint32_t empty0 = tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0);
-        const uint32_t empty1 = tc::mapa(tc::smem_u32(&sh->tmem_empty[1]), 0);
-        for (uint32_t tile = seq; tile < ntiles; tile += nseq, ++t) {
-            const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+        for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
             const bool row_ok = am >= 0;
             const int am_min = __reduce_min_sync(0xffffffffu, row_ok ? am : 2147483647);
@@ -258,11 +262,12 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();
             uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ACC_COL0 + buf * TILE_N + col0, v);
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col0 + buf * TILE_N + col0, v);
             tc::tmem_ld_wait();
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive_cluster(buf ? empty1 : empty0);  // accumulator is in registers
+            if (lane == 0) tc::mbar_arrive_cluster(empty0 + buf * 8u);  // accumulator is in registers
+            if (++buf == NBUF) { buf = 0; bph ^= 1; }
             // sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once
             int any = 0;
 #pragma unroll
@@ -285,17 +290,20 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
     if (warp == 1) tc::tmem_dealloc_cta2(tmem_base, TMEM_COLS);
 }
 
-template <int METRIC, int CPS>
-int launch_ts(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, int q0, int groups, int kchunks, cudaStream_t s) {
-    constexpr int STAGE_BYTES = CPS * BOX_BYTES;
+template <int METRIC, int CPS, int TN, int NBUF>
+int launch_ts(const Index &ix, const ScanArgs &a, int q0, int groups, int kchunks, cudaStream_t s) {
+    constexpr int ROWS_CTA = TN / 2;
+    constexpr int STAGE_BYTES = CPS * ROWS_CTA * CHUNK_BYTES;
+    CUtensorMap mrows;
+    PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, ROWS_CTA));
     const size_t ctrl = sizeof(TsShared);
     int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE_BYTES);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (ix.opt.ts_stages > 1 && ix.opt.ts_stages < stages) stages = ix.opt.ts_stages;
     const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + ctrl;
-    auto kernel = scan_i8_ts_kernel<METRIC, CPS>;
+    auto kernel = scan_i8_ts_kernel<METRIC, CPS, TN, NBUF>;
     PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t ntiles = (a.row_end - a.row_begin + TILE_N - 1) / TILE_N;
+    const uint32_t ntiles = (a.row_end - a.row_begin + TN - 1) / TN;
     uint32_t pairs = (uint32_t)ix.sm_count / 2;
     pairs = pairs / groups * groups;
     const uint32_t want = ntiles * (uint32_t)groups;  // one tile sequence per tile at most
@@ -314,6 +322,17 @@ int launch_ts(const Index &ix, const ScanArgs &a, const CUtensorMap &mrows, int 
     cfg.numAttrs = 1;
     PKV_CUDA(cudaLaunchKernelEx(&cfg, kernel, mrows, a, q0, groups, kchunks, stages));
     return PKV_OK;
+}
+
+// Tile shape by what TMEM has left behind the query columns (dim_pad/4, rounded up to 32):
+// >= 384 columns: three 128-row accumulators; >= 288: three 96-row ones; else two 128-row ones.
+template <int METRIC, int CPS>
+int launch_ts_shape(const Index &ix, const ScanArgs &a, int q0, int groups, int kchunks, cudaStream_t s) {
+    const int free_cols = TMEM_COLS - (ix.dim_pad / 4 + 31) / 32 * 32;
+    const int nbuf_opt = ix.opt.ts_acc_buffers;
+    if (nbuf_opt != 2 && free_cols >= 384) return launch_ts<METRIC, CPS, 128, 3>(ix, a, q0, groups, kchunks, s);
+    if (nbuf_opt != 2 && free_cols >= 288) return launch_ts<METRIC, CPS, 96, 3>(ix, a, q0, groups, kchunks, s);
+    return launch_ts<METRIC, CPS, 128, 2>(ix, a, q0, groups, kchunks, s);
 }
 
 }  // namespace
@@ -336,12 +355,10 @@ int launch_scan_ts(const Index &ix, const ScanArgs &a, int q0, cudaStream_t s) {
     const int gmax = scan_ts_queries_per_launch(ix) / QM;
     if (groups > gmax) groups = gmax;
     if (groups < 1) groups = 1;
-    CUtensorMap mrows;
-    PKV_TRY(make_tmap_bytes(&mrows, ix.d_data, (uint64_t)ix.dim_pad, (uint64_t)ix.sealed_rows, (uint64_t)ix.pitch, ROWS_CTA));
     int cps = ix.opt.ts_chunks > 0 ? ix.opt.ts_chunks : (kchunks % 3 == 0 ? 3 : 2);
     if (cps > kchunks) cps = kchunks;
 #define PKV_TS_CASE(M, C) \
-    if (a.metric == M && cps == C) return launch_ts<M, C>(ix, a, mrows, q0, groups, kchunks, s)
+    if (a.metric == M && cps == C) return launch_ts_shape<M, C>(ix, a, q0, groups, kchunks, s)
     PKV_TS_CASE(PKV_COSINE, 1); PKV_TS_CASE(PKV_COSINE, 2); PKV_TS_CASE(PKV_COSINE, 3); PKV_TS_CASE(PKV_COSINE, 4);
     PKV_TS_CASE(PKV_L2, 1); PKV_TS_CASE(PKV_L2, 2); PKV_TS_CASE(PKV_L2, 3); PKV_TS_CASE(PKV_L2, 4);
     PKV_TS_CASE(PKV_DOT, 1); PKV_TS_CASE(PKV_DOT, 2); PKV_TS_CASE(PKV_DOT, 3); PKV_TS_CASE(PKV_DOT, 4);
