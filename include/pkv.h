@@ -234,14 +234,18 @@ typedef struct {
     double last_scan_ms;        /* CUDA-event time of the scan kernels of the last search on this thread */
     double last_total_ms;       /* CUDA-event time of the last search's device work */
     int32_t last_scan_kind;     /* which scan kernel family ran: 1 simt-f32, 2 simt-i8, 3 tc-i8, 4 tc-tf32, 5 simt-f16,
-                                   6 tc-f16 (f16 rows), 7 tc-f16 on the fp16 image of f32 rows */
+                                   6 tc-f16 (f16 rows), 7 tc-f16 on the fp16 image of f32 rows,
+                                   8 tc-i8 on the int8 image of f32/f16 rows (pkv_scan_img8.cu) */
     int32_t reserved;
     int64_t combined_searches;  /* host searches that shared one corpus scan with concurrent callers */
 } pkv_counters;
 int pkv_index_counters(pkv_index *h, pkv_counters *out);
-/* Tuning knobs for tests and the bench: "force_simt", "use_shadow", "tc_cta2", "tc_min_queries",
- * "tc_min_queries_f32", "tc_min_queries_img", "candidate_capacity", "first_chunk_rows",
- * "chunk_growth_x100", "optimistic", "simt_bootstrap", "combine", "time_kernels", "tc_prefetch_tiles". */
+/* Tuning knobs for tests and the bench: "image_mask" (which filter images an f32/f16
+ * index builds at seal: bit 1 int8, bit 0 fp16; set before the first append), "use_shadow" (-1 best available,
+ * 2 int8 image, 1 fp16 image, 0 none), "img8_max_queries", "img8_peak_sigma_x10", "force_simt", "tc_ts",
+ * "ts_groups", "ts_chunks", "ts_stages", "ts_acc_buffers", "tc_cta2", "tc_min_queries", "tc_min_queries_f32",
+ * "tc_min_queries_img", "candidate_capacity", "first_chunk_rows", "chunk_growth_x100", "optimistic",
+ * "simt_bootstrap", "combine", "time_kernels", "tc_prefetch_tiles".  Unknown names are PKV_ERR_INVALID. */
 int pkv_index_set_option(pkv_index *h, const char *name, int64_t value);
 
 /* -- PQL operator policy: pql/preprocess.rs:314-465, builder/filters/embedding_types.rs --- */
