@@ -196,7 +196,8 @@ struct Options {
     int tc_ts = 1;                   // int8, > 128 queries: queries resident in TMEM (pkv_scan_ts.cu)
     int ts_groups = 4;               // 256-query groups served by one launch of that kernel (row tiles shared through L2)
     int ts_stages = 0;               // 0 = as many row stages as fit
-    int ts_acc_buffers = 0;          // 0 = three accumulator buffers when TMEM has room, 2 = always two (A/B experiments)
+    int ts_acc_buffers = 0;          // 0 = three 128-row accumulator buffers when TMEM has room (D <= 512) else two,
+                                     // 2 = always two, 3 = three whenever possible (96-row tiles up to D = 896)
     int ts_chunks = 0;               // K-chunks (8 KB boxes) per stage: 0 = auto (3 when they divide the row, else 2)
     int tc_min_queries = 1;          // int8: the TMA/tcgen05 kernel streams at ~95% of HBM peak even for one query
 };

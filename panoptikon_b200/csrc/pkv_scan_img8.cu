@@ -241,11 +241,25 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         const int qrow = q < a.nq ? q : (a.nq - 1);
         const uint8_t *qp = (const uint8_t *)im.q8 + (size_t)qrow * im.dim_pad8;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int c8 = (ew >> 2); c8 < im.dim_pad8 / 32; c8 += EPI_WARPS / 4) {
-            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32));
-            const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32 + 16));
-            const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            tc::tmem_st_32x8(lane_addr + (uint32_t)c8 * 8, v);
+        // all global loads first (<= 8 chunks of 32 codes per warp for D <= 1024), then the TMEM stores: the
+        // prologue pays one memory latency instead of one per chunk
+        const int n8 = im.dim_pad8 / 32;
+        uint4 qlo[8], qhi[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int c8 = (ew >> 2) + it * (EPI_WARPS / 4);
+            if (c8 < n8) {
+                qlo[it] = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32));
+                qhi[it] = __ldg(reinterpret_cast<const uint4 *>(qp + c8 * 32 + 16));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int c8 = (ew >> 2) + it * (EPI_WARPS / 4);
+            if (c8 < n8) {
+                const uint32_t v[8] = {qlo[it].x, qlo[it].y, qlo[it].z, qlo[it].w, qhi[it].x, qhi[it].y, qhi[it].z, qhi[it].w};
+                tc::tmem_st_32x8(lane_addr + (uint32_t)c8 * 8, v);
+            }
         }
         tc::tmem_st_wait();
     }
@@ -590,7 +604,8 @@ int launch_img8_shape(const Index &ix, const ScanArgs &a, const ImgArgs &im, int
     const int free_cols = TMEM_COLS - (ix.dim_pad8 / 4 + 31) / 32 * 32;
     const int nbuf_opt = ix.opt.ts_acc_buffers;
     if (nbuf_opt != 2 && free_cols >= 384) return launch_img8<METRIC, CPS, PAIR, 128, 3>(ix, a, im, q0, groups, kchunks, s);
-    if (nbuf_opt != 2 && free_cols >= 288) return launch_img8<METRIC, CPS, PAIR, 96, 3>(ix, a, im, q0, groups, kchunks, s);
+    if (nbuf_opt == 3 && free_cols >= 288) return  // measured 1-3 % slower than two 128-row buffers at D=768
+        launch_img8<METRIC, CPS, PAIR, 96, 3>(ix, a, im, q0, groups, kchunks, s);
     return launch_img8<METRIC, CPS, PAIR, 128, 2>(ix, a, im, q0, groups, kchunks, s);
 }
 

@@ -148,3 +148,15 @@ def test_ts_chunks_per_stage(dim, chunks):
         got = ix.search(qc, 40, pk.COSINE)
         assert ix.counters().last_scan_kind == 3
     assert_exact(got, orc.topk(xc, qc, orc.COSINE, 40, threads=16))
+
+
+@pytest.mark.parametrize("buffers", [2, 3])
+@pytest.mark.parametrize("dim", [512, 768, 896, 1024])
+def test_ts_accumulator_buffer_shapes(dim, buffers):
+    # 3 buffers: 128-row tiles up to D=512, 96-row tiles up to D=896, else 2 x 128 rows; all must agree with the oracle
+    x, q, scale, xc, qc = int8_space(20017, dim, 161, 300)
+    with _index(xc, scale) as ix:
+        ix.set_option("ts_acc_buffers", buffers)
+        got = ix.search(qc, 50, pk.L2)
+        assert ix.counters().last_scan_kind == 3
+    assert_exact(got, orc.topk(xc, qc, orc.L2, 50, threads=16))

@@ -226,3 +226,14 @@ def test_img8_peaky_and_sparse_rows():
             got = ix.search(q, 60, metric)
             assert ix.counters().last_scan_kind == 8
             assert_close_topk(got, orc.topk(x, q, metric, 60, threads=8), x, q, metric)
+
+
+@pytest.mark.parametrize("buffers", [2, 3])
+@pytest.mark.parametrize("nq", [20, 300])
+def test_img8_accumulator_buffer_shapes(nq, buffers):
+    x, q = orc.synthetic(30011, 768, 311), orc.synthetic(nq, 768, 312)
+    with _index(x) as ix:
+        ix.set_option("ts_acc_buffers", buffers)
+        got = ix.search(q, 40, pk.COSINE)
+        assert ix.counters().last_scan_kind == 8
+    assert_close_topk(got, orc.topk(x, q, orc.COSINE, 40, threads=16), x, q, orc.COSINE)
