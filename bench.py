@@ -472,6 +472,55 @@ def main():
         "overflow_rescans": int(c1.fallback_queries - c0.fallback_queries),
     }
 
+    # ---- full-size properties of the last batch's result (the oracle cannot scan 10M rows in the time budget):
+    # sorted, unique, idempotent, and a sampled exactness certificate - the distance of every returned row and of
+    # 4096 random rows of this shard is recomputed from the STORED rows in float64 with torch; returned distances
+    # must match and no sampled row outside the result may beat the k-th best.
+    if world == 1:
+        try:
+            qd = q_dev[(a.steps - 1) % n_q_sets]
+            ids, dst, cnt = (t.clone() for t in ix.search(qd, a.k, metric_code, bitmap=bm_dev))
+            ids2, dst2, _ = ix.search(qd, a.k, metric_code, bitmap=bm_dev)
+            full = bool((cnt == a.k).all().item())
+            props = {"sorted": bool((dst[:, 1:] >= dst[:, :-1]).all().item()) if full else None,
+                     "unique_ids": bool(all(len(set(r)) == len(r) for r in ids[:8].cpu().tolist())),
+                     "idempotent": bool(torch.equal(ids, ids2) and torch.equal(dst.view(torch.int32), dst2.view(torch.int32)))}
+            g = torch.Generator(device=dev)
+            g.manual_seed(12345)
+            sample_rows = torch.randint(0, r1 - r0, (4096,), generator=g, device=dev)
+            nqc = min(a.batch, 64)                                   # certificate on the first 64 queries
+
+            def exact(rows_idx, qq):
+                xr = ix.get_rows(rows_idx).to(torch.float64)
+                if a.dtype == "i8":
+                    qq = qq.to(torch.float64)
+                else:
+                    qq = qq.to(torch.float64)
+                dots = qq @ xr.T
+                if a.metric == "dot":
+                    return -dots
+                if a.metric == "cosine":
+                    return 1.0 - dots / (qq.norm(dim=1, keepdim=True) * xr.norm(dim=1)[None, :])
+                return torch.cdist(qq, xr)
+
+            qs64 = qd[:nqc]
+            d_samp = exact(sample_rows, qs64)                         # [nqc, 4096]
+            if bm_dev is not None:
+                member = ((bm_dev[sample_rows >> 6] >> (sample_rows & 63)) & 1).bool()
+                d_samp[:, ~member] = float("inf")
+            kth = dst[:nqc, a.k - 1].to(torch.float64)
+            tol = 1e-5 * torch.maximum(kth.abs(), (1.0 - kth).abs() if a.metric == "cosine" else kth.abs()) + 1e-7
+            in_result = (sample_rows[None, None, :] == (ids[:nqc] - r0)[:, :, None]).any(dim=1)
+            beaten = ((d_samp < (kth - tol)[:, None]) & ~in_result).sum().item()
+            d_ret = torch.stack([exact((ids[i] - r0).clamp(min=0), qs64[i:i + 1])[0] for i in range(min(nqc, 8))])
+            err = ((d_ret - dst[:min(nqc, 8)].to(torch.float64)).abs() /
+                   torch.maximum(d_ret.abs(), (1.0 - d_ret).abs() if a.metric == "cosine" else d_ret.abs()).clamp(min=1e-30))
+            props.update({"sampled_rows_beating_kth": int(beaten), "returned_distance_max_rel_err": float(err.max().item()),
+                          "checked": f"{nqc} queries x 4096 random rows + the returned rows of 8 queries, float64 from the stored rows"})
+            line["full_size_properties"] = props
+        except Exception as e:  # the properties are a report, never a reason to lose the bench line
+            line["full_size_properties"] = {"error": repr(e)}
+
     # ---- CPU baseline on a bounded sample of the same corpus + parity of the GPU path on that sample
     if not a.no_cpu and sample_host and a.bitmap_density == 0:
         from oracle import oracle as orc
