@@ -286,8 +286,9 @@ def main():
                torch.empty((a.batch, a.k), dtype=torch.float32, device=dev),
                torch.empty(a.batch, dtype=torch.int32, device=dev))
     if world > 1:
-        g_ids = torch.empty((world, a.batch, a.k), dtype=torch.int64, device=dev)
-        g_dist = torch.empty((world, a.batch, a.k), dtype=torch.float32, device=dev)
+        merged_out = (torch.empty((a.batch, a.k), dtype=torch.int64, device=dev),
+                      torch.empty((a.batch, a.k), dtype=torch.float32, device=dev),
+                      torch.empty(a.batch, dtype=torch.int32, device=dev))
         packed = torch.empty((a.batch, a.k, 3), dtype=torch.int32, device=dev)       # ids(2 words) + dist
         g_packed = torch.empty((world, a.batch, a.k, 3), dtype=torch.int32, device=dev)
 
@@ -306,14 +307,12 @@ def main():
         ids, dst, cnt = ix.search(q, a.k, metric_code, out=out_dev, bitmap=bm_dev)
         if world == 1:
             return ids, dst, cnt
-        # ONE all-gather of the per-shard candidates (ids and distances packed side by side)
-        packed[..., :2] = ids.view(torch.int32).view(a.batch, a.k, 2)
-        packed[..., 2] = dst.view(torch.int32)
+        # ONE all-gather of the per-shard candidates: a pack kernel (12-byte entries), the collective, and a merge
+        # kernel that reads the gathered buffer directly - three stream operations per step
+        pk.pack_topk(ids, dst, out=packed, device=local_rank)
         dist.all_gather_into_tensor(g_packed, packed)
-        g_ids.copy_(g_packed[..., :2].contiguous().view(torch.int64).view(world, a.batch, a.k))
-        g_dist.copy_(g_packed[..., 2].contiguous().view(torch.float32))
-        merge_launches[0] += 1
-        return pk.merge_topk(g_ids, g_dist, device=local_rank)
+        merge_launches[0] += 2
+        return pk.merge_packed(g_packed, out=merged_out, device=local_rank)
 
     def barrier():
         if world > 1:

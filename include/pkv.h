@@ -217,6 +217,13 @@ int pkv_fuse_ranks(int mode, int n_lists, const int64_t *const *groups, const in
 int pkv_merge_topk_device(int device, const int64_t *d_ids, const float *d_dist, int parts, int nq, int k,
                           int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts, void *stream);
 
+/* The same exchange without intermediate copies: pack a shard's nq*k results into 12-byte entries
+ * {id low word, id high word, distance bits} (the payload of the ONE all-gather), and merge the gathered
+ * [parts][nq][k] packed buffer directly.  Both only ENQUEUE on `stream` (no host synchronisation). */
+int pkv_pack_topk_device(int device, const int64_t *d_ids, const float *d_dist, int64_t n, void *d_packed, void *stream);
+int pkv_merge_packed_device(int device, const void *d_packed, int parts, int nq, int k, int64_t *d_out_ids,
+                            float *d_out_dist, int32_t *d_out_counts, void *stream);
+
 /* Per-item aggregation of row distances (builder/filters/exact.rs:67-80):
  * agg 0 MIN / 1 MAX / 2 AVG of d grouped by item, or SUM(d*w)/SUM(w) when d_weights
  * is non-NULL.  item ids are dense 0..n_items-1; NaN rows are skipped (SQL NULL);

@@ -89,6 +89,8 @@ SIGNATURES = {
     "pkv_index_get_rows_device": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "pkv_fuse_ranks": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "pkv_merge_topk_device": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pkv_pack_topk_device": (C.c_int, [C.c_int, _P, _P, C.c_int64, _P, _P]),
+    "pkv_merge_packed_device": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pkv_aggregate_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "pkv_index_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "pkv_index_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),

@@ -1008,6 +1008,21 @@ int pkv_merge_topk_device(int device, const int64_t *d_ids, const float *d_dist,
     return PKV_OK;
 }
 
+int pkv_pack_topk_device(int device, const int64_t *d_ids, const float *d_dist, int64_t n, void *d_packed, void *stream) {
+    PKV_TRY(use_device(device));
+    if (n < 0) return fail(PKV_ERR_INVALID, "n must be >= 0");
+    if (n > 0 && (!d_ids || !d_dist || !d_packed)) return fail(PKV_ERR_INVALID, "NULL buffer");
+    return launch_pack_topk(d_ids, d_dist, n, d_packed, (cudaStream_t)stream);
+}
+
+int pkv_merge_packed_device(int device, const void *d_packed, int parts, int nq, int k, int64_t *d_out_ids,
+                            float *d_out_dist, int32_t *d_out_counts, void *stream) {
+    PKV_TRY(use_device(device));
+    if (parts < 1 || parts > 256 || nq < 0 || k < 1) return fail(PKV_ERR_INVALID, "bad merge shape");
+    if (nq > 0 && (!d_packed || !d_out_ids || !d_out_dist || !d_out_counts)) return fail(PKV_ERR_INVALID, "NULL buffer");
+    return launch_merge_packed(d_packed, parts, nq, k, d_out_ids, d_out_dist, d_out_counts, (cudaStream_t)stream);
+}
+
 int pkv_aggregate_device(int device, const float *d_dist, const int64_t *d_item_of_row, const float *d_weights,
                          int64_t n, int64_t n_items, int agg, double *d_out, void *stream) {
     PKV_TRY(use_device(device));

@@ -300,6 +300,9 @@ int launch_finalize(const Index &ix, Workspace &ws, int nq, int k, int64_t *d_id
 int launch_row_mags(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);
 int launch_merge(const int64_t *d_ids, const float *d_dist, int parts, int nq, int k, int64_t *o_ids, float *o_dist,
                  int32_t *o_counts, cudaStream_t s);
+int launch_pack_topk(const int64_t *d_ids, const float *d_dist, int64_t n, void *d_packed, cudaStream_t s);
+int launch_merge_packed(const void *d_packed, int parts, int nq, int k, int64_t *o_ids, float *o_dist, int32_t *o_counts,
+                        cudaStream_t s);
 int launch_aggregate(const float *d_dist, const int64_t *d_item, const float *d_w, int64_t n, int64_t n_items, int agg,
                      double *d_out, cudaStream_t s);
 int launch_absmax(const float *d_values, int64_t n, float *d_out, cudaStream_t s);

@@ -304,6 +304,64 @@ __global__ void merge_kernel(const int64_t *ids, const float *dist, int parts, i
     if (threadIdx.x == 0) o_counts[q] = m;
 }
 
+// Packed shard results: 12 bytes per entry {id low word, id high word, distance bits}, the payload of the ONE
+// all-gather; the merge reads the gathered buffer directly (no unpacking pass).
+__global__ void pack_topk_kernel(const int64_t *ids, const float *dist, int64_t n, uint32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t id = (uint64_t)ids[i];
+    out[3 * i] = (uint32_t)id;
+    out[3 * i + 1] = (uint32_t)(id >> 32);
+    out[3 * i + 2] = __float_as_uint(dist[i]);
+}
+__device__ __forceinline__ int64_t packed_id(const uint32_t *e) { return (int64_t)((uint64_t)e[0] | ((uint64_t)e[1] << 32)); }
+__device__ int packed_valid_len(const uint32_t *list, int k) {
+    int lo = 0, hi = k;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (packed_id(list + 3 * (size_t)mid) == -1) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+__global__ void merge_packed_kernel(const uint32_t *packed, int parts, int nq, int k, int64_t *o_ids, float *o_dist,
+                                    int32_t *o_counts) {
+    const int q = blockIdx.x;
+    extern __shared__ int s_len[];  // [parts]
+    if ((int)threadIdx.x < parts) s_len[threadIdx.x] = packed_valid_len(packed + 3 * (((size_t)threadIdx.x * nq + q) * k), k);
+    __syncthreads();
+    int total = 0;
+    for (int p = 0; p < parts; ++p) total += s_len[p];
+    const int m = total < k ? total : k;
+    for (int e = threadIdx.x; e < parts * k; e += blockDim.x) {
+        const int p = e / k, i = e - p * k;
+        if (i >= s_len[p]) continue;
+        const uint32_t *mine_e = packed + 3 * (((size_t)p * nq + q) * k + i);
+        const uint32_t mine = ordered_bits(__uint_as_float(mine_e[2]));
+        int rank = i;
+        for (int o = 0; o < parts; ++o) {
+            if (o == p) continue;
+            const uint32_t *ol = packed + 3 * (((size_t)o * nq + q) * k);
+            int lo = 0, hi = s_len[o];
+            while (lo < hi) {  // o < p: count entries <= mine; o > p: count entries < mine
+                int mid = (lo + hi) >> 1;
+                uint32_t v = ordered_bits(__uint_as_float(ol[3 * (size_t)mid + 2]));
+                bool before = o < p ? v <= mine : v < mine;
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            o_ids[(size_t)q * k + rank] = packed_id(mine_e);
+            o_dist[(size_t)q * k + rank] = __uint_as_float(mine_e[2]);
+        }
+    }
+    for (int i = m + threadIdx.x; i < k; i += blockDim.x) {
+        o_ids[(size_t)q * k + i] = -1;
+        o_dist[(size_t)q * k + i] = __int_as_float(0x7fc00000);
+    }
+    if (threadIdx.x == 0) o_counts[q] = m;
+}
+
 // -------------------------------------------------------------- aggregation
 __device__ __forceinline__ void atomic_min_f64(double *addr, double v) {
     unsigned long long *a = (unsigned long long *)addr;
@@ -455,6 +513,22 @@ int launch_merge(const int64_t *d_ids, const float *d_dist, int parts, int nq, i
                  int32_t *o_counts, cudaStream_t s) {
     if (nq <= 0) return PKV_OK;
     merge_kernel<<<nq, 256, parts * sizeof(int), s>>>(d_ids, d_dist, parts, nq, k, o_ids, o_dist, o_counts);
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
+int launch_pack_topk(const int64_t *d_ids, const float *d_dist, int64_t n, void *d_packed, cudaStream_t s) {
+    if (n <= 0) return PKV_OK;
+    pack_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_ids, d_dist, n, (uint32_t *)d_packed);
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
+int launch_merge_packed(const void *d_packed, int parts, int nq, int k, int64_t *o_ids, float *o_dist, int32_t *o_counts,
+                        cudaStream_t s) {
+    if (nq <= 0) return PKV_OK;
+    merge_packed_kernel<<<nq, 256, parts * sizeof(int), s>>>((const uint32_t *)d_packed, parts, nq, k, o_ids, o_dist,
+                                                             o_counts);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }

@@ -274,6 +274,37 @@ def merge_topk(ids, dist, device: int = 0):
     return o_ids, o_dist, o_cnt
 
 
+def pack_topk(ids, dist, out=None, device: int = 0):
+    """[nq,k] int64 ids + [nq,k] f32 distances (torch CUDA) -> [nq,k,3] int32 packed entries, the payload of the
+    one all-gather.  Enqueued on the current stream."""
+    import torch
+
+    nq, k = ids.shape
+    if out is None:
+        out = torch.empty((nq, k, 3), dtype=torch.int32, device=ids.device)
+    stream = torch.cuda.current_stream(ids.device).cuda_stream
+    N.check(N.lib().pkv_pack_topk_device(device, C.c_void_p(ids.data_ptr()), C.c_void_p(dist.data_ptr()), nq * k,
+                                         C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+    return out
+
+
+def merge_packed(packed, out=None, device: int = 0):
+    """packed: [parts,nq,k,3] int32 as gathered from the row shards -> (ids, dist, counts) of the global top-k.
+    Enqueued on the current stream."""
+    import torch
+
+    parts, nq, k, _ = packed.shape
+    if out is None:
+        out = (torch.empty((nq, k), dtype=torch.int64, device=packed.device),
+               torch.empty((nq, k), dtype=torch.float32, device=packed.device),
+               torch.empty(nq, dtype=torch.int32, device=packed.device))
+    stream = torch.cuda.current_stream(packed.device).cuda_stream
+    N.check(N.lib().pkv_merge_packed_device(device, C.c_void_p(packed.data_ptr()), parts, nq, k,
+                                            C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                            C.c_void_p(out[2].data_ptr()), C.c_void_p(stream)))
+    return out
+
+
 def aggregate(dist, item_of_row, n_items: int, agg: int, weights=None, device: int = 0):
     """Per-item MIN/MAX/AVG (or weighted mean) of row distances; torch CUDA tensors."""
     import torch

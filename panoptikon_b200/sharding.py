@@ -36,7 +36,7 @@ def unpack_results(packed):
     return ids, dist
 
 
-def gather_and_merge(ids, dist, merge: Callable, group=None):
+def gather_and_merge(ids, dist, merge: Callable = None, group=None):
     """All ranks contribute their shard's (ids, dist); every rank gets the merged global top-k.
     `merge(ids[parts,nq,k], dist[parts,nq,k]) -> (ids, dist, counts)`; on GPUs pass
     panoptikon_b200.merge_topk."""
@@ -44,6 +44,16 @@ def gather_and_merge(ids, dist, merge: Callable, group=None):
     import torch.distributed as dist_mod
 
     world = dist_mod.get_world_size(group)
+    if ids.is_cuda and merge is None:
+        # GPU fast path: one pack kernel, ONE all-gather, one merge kernel reading the gathered buffer directly
+        import panoptikon_b200 as pk
+
+        dev = ids.device.index or 0
+        packed = pk.pack_topk(ids, dist, device=dev)
+        nq, k, _ = packed.shape
+        gathered = torch.empty((world, nq, k, 3), dtype=torch.int32, device=packed.device)
+        dist_mod.all_gather_into_tensor(gathered, packed, group=group)
+        return pk.merge_packed(gathered, device=dev)
     packed = pack_results(ids, dist)
     nq, k, _ = packed.shape
     gathered = torch.empty((world * nq, k, 3), dtype=torch.int32, device=packed.device)  # rank-major concat

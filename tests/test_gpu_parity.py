@@ -315,3 +315,31 @@ def test_int8_wide_rows_fall_back_to_cuda_cores():
         for metric in METRICS:
             assert_exact(ix.search(qc, 40, metric), orc.topk(xc, qc, metric, 40, threads=8))
         assert ix.counters().last_scan_kind == 2
+
+
+def test_packed_shard_exchange_matches_plain_merge():
+    # two shards of one corpus on one GPU: pack -> (concatenation = what the all-gather delivers) -> merge of the
+    # packed buffer must equal the unpacked merge and the search over the whole corpus
+    import torch
+
+    x = orc.synthetic(30000, 64, 71)
+    q = orc.synthetic(37, 64, 72)
+    parts = []
+    for b, e in ((0, 17000), (17000, 30000)):
+        ix = pk.VectorIndex(64, pk.F32)
+        ix.set_row_base(b)
+        ix.append(x[b:e])
+        ix.seal()
+        with ix:
+            ids, dd, _ = ix.search(torch.from_numpy(q).cuda(), 25, pk.COSINE)
+            parts.append((ids.clone(), dd.clone()))
+    g_ids = torch.stack([p[0] for p in parts])
+    g_dist = torch.stack([p[1] for p in parts])
+    plain = pk.merge_topk(g_ids, g_dist)
+    packed = torch.stack([pk.pack_topk(i, d) for i, d in parts])
+    fast = pk.merge_packed(packed)
+    torch.cuda.synchronize()
+    assert torch.equal(plain[0], fast[0]) and torch.equal(plain[2], fast[2])
+    assert torch.equal(plain[1].view(torch.int32), fast[1].view(torch.int32))
+    want = orc.topk(x, q, orc.COSINE, 25, threads=8)
+    assert_close_topk(tuple(t.cpu().numpy() for t in fast), want, x, q, orc.COSINE)

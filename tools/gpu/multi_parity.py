@@ -27,6 +27,9 @@ for dtype, data, queries in ((pk.I8, xc, qc), (pk.F32, x, q)):
     for metric in (pk.COSINE, pk.L2):
         ids, dd, _ = ix.search(torch.from_numpy(queries).cuda(), k, metric)
         m_ids, m_dist, m_cnt = sharding.gather_and_merge(ids, dd, lambda i, s: pk.merge_topk(i, s, device=local))
+        f_ids, f_dist, f_cnt = sharding.gather_and_merge(ids, dd)   # pack kernel + one all-gather + merge of the packed buffer
+        assert torch.equal(m_ids, f_ids) and torch.equal(m_cnt, f_cnt)
+        assert torch.equal(m_dist.view(torch.int32), f_dist.view(torch.int32))
         if rank == 0:
             got = (m_ids.cpu().numpy(), m_dist.cpu().numpy(), m_cnt.cpu().numpy())
             want = orc.topk(data, queries, metric, k, threads=16)
