@@ -327,8 +327,13 @@ restart:
         if (chunk >= 1024) chunk = chunk / 128 * 128;
         if (chunk > N - pos) chunk = N - pos;
         if (chunk < 1) chunk = 1;
-        const bool sync = !(optimistic && r.min_filled >= (uint32_t)k && pos > 0);
+        // Every row of the threshold-less first chunk becomes a candidate of every query, so with >= k rows each
+        // query has its k-th best afterwards: no host round trip is needed to learn that.  (If that ever failed
+        // the thresholds would stay +inf, the next chunk would overflow, and the sticky flag redoes the search.)
+        const bool first_fill = optimistic && pos == 0 && r.min_filled < (uint32_t)k && chunk >= k;
+        const bool sync = !(optimistic && (first_fill || (r.min_filled >= (uint32_t)k && pos > 0)));
         PKV_TRY(scan_range(r, pos, pos + chunk, sync));
+        if (first_fill) r.min_filled = (uint32_t)k;
         pos += chunk;
     }
     if (r.unsynced > 0) {
