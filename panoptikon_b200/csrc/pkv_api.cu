@@ -31,7 +31,9 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
-static int use_device(int device) {
+// Makes `device` current for the duration of one API call and restores the caller's device afterwards
+// (a server thread or a torch process may hold indexes on several GPUs).
+int DeviceGuard::use(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) {
@@ -40,9 +42,30 @@ static int use_device(int device) {
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
     if (device < 0 || device >= count) return fail(PKV_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
-    PKV_CUDA(cudaSetDevice(device));
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+        cudaGetLastError();
+        cur = -1;
+    }
+    if (cur != device) {
+        PKV_CUDA(cudaSetDevice(device));
+        if (prev < 0) prev = cur;
+    }
     return PKV_OK;
 }
+DeviceGuard::~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+}
+#define PKV_USE_DEVICE(dev) \
+    ::pkv::DeviceGuard _device_guard; \
+    PKV_TRY(_device_guard.use(dev))
+
+// figures of the last search issued by the calling thread (pkv_counters.last_*)
+struct LastSearch {
+    double scan_ms = 0, total_ms = 0;
+    int kind = 0;
+};
+static thread_local LastSearch g_last;
 
 static int elem_size(int dtype) { return dtype == PKV_F32 ? 4 : (dtype == PKV_I8 ? 1 : 2); }
 static int pad_dim(int dim, int dtype) {
@@ -175,16 +198,28 @@ struct SearchRun {
     int nq, k;
     int64_t safe_rows;
     uint32_t min_filled = 0;
+    uint32_t last_max_raw = 0;  // largest per-query push count of the last synced chunk
     double scan_ms = 0;
     int launches = 0, scan_launches = 0;
     int depth_overflows = 0;
     bool use_tc = false, use_tc_f32 = false;
-    int unsynced = 0;  // chunks enqueued since the last host sync
+    bool live_capable = false;  // the scan kernels of this search can maintain the thresholds themselves
+    int unsynced = 0;           // chunks enqueued since the last host sync
+    // result buffers: the select behind the LAST chunk writes them itself (no finalize launch)
+    int64_t *d_ids = nullptr;
+    float *d_dist = nullptr;
+    int32_t *d_counts = nullptr;
+    bool outputs_written = false;
 };
 
-static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
+// One chunk: scan kernel(s) over rows [b, e), then the select.
+//   sync : wait for the chunk and read its status (splits the range when a candidate buffer overflowed)
+//   live : the scan maintains the thresholds in-kernel (one launch for all remaining rows)
+//   last : no chunk follows: the select writes the result rows
+static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync, bool live, bool last) {
     r.args.row_begin = (uint32_t)b;
     r.args.row_end = (uint32_t)e;
+    r.args.topk.live = live ? 1 : 0;
     const bool timed = r.ix.opt.time_kernels != 0;
     cudaEvent_t ev_begin = r.ws.ev[0], ev_end = r.ws.ev[1];
     if (!sync && timed) {
@@ -214,7 +249,11 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
     r.launches += n;
     r.scan_launches += n;
     if (timed) PKV_CUDA(cudaEventRecord(ev_end, r.s));
-    PKV_TRY(launch_select(r.ix, r.ws, r.nq, r.k, r.args.metric, r.fs, r.s));
+    // a chunk that may be followed by a live launch leaves KEY_MAX behind the kept keys (append-only buffers)
+    const bool write_out = last && !sync;  // a synced chunk may still be split and re-scanned
+    PKV_TRY(launch_select(r.ix, r.ws, r.nq, r.k, r.fs, /*clear_tail=*/r.live_capable && !last, write_out ? r.d_ids : nullptr,
+                          r.d_dist, r.d_counts, r.s));
+    if (write_out) r.outputs_written = true;
     r.launches += sync ? 2 : 1;
     if (!sync) {
         r.unsynced++;
@@ -229,6 +268,7 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
     }
     const SearchStatus st = *r.ws.h_status;
     r.min_filled = st.min_filled;
+    r.last_max_raw = st.max_raw_cnt;
     static const bool trace = getenv("PKV_TRACE") != nullptr;
     if (trace && timed) {
         float ms = 0.f, ms2 = 0.f;
@@ -236,9 +276,9 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
         cudaEventRecord(r.ws.ev[0], r.s);
         cudaEventSynchronize(r.ws.ev[0]);
         cudaEventElapsedTime(&ms2, r.ws.ev[1], r.ws.ev[0]);
-        fprintf(stderr, "[pkv] rows [%lld,%lld) nq %d: scan %.3f ms (%.0f GB/s), select+sync %.3f ms, max_raw_cnt %u, overflow %u\n",
-                (long long)b, (long long)e, r.nq, ms, (double)(e - b) * r.ix.pitch / (ms * 1e6), ms2, st.max_raw_cnt,
-                st.any_overflow);
+        fprintf(stderr, "[pkv] rows [%lld,%lld) nq %d%s: scan %.3f ms (%.0f GB/s), select+sync %.3f ms, max_raw_cnt %u, overflow %u\n",
+                (long long)b, (long long)e, r.nq, live ? " live" : "", ms, (double)(e - b) * r.ix.pitch / (ms * 1e6), ms2,
+                st.max_raw_cnt, st.any_overflow);
     }
     if (st.any_overflow) {
         // Some query pushed more candidates than its buffer holds.  The select kept the best k
@@ -251,10 +291,17 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync = true) {
         int64_t mid = b + (e - b) / 2;
         mid = (mid + 127) / 128 * 128;
         if (mid <= b || mid >= e) mid = b + (e - b) / 2;
-        PKV_TRY(scan_range(r, b, mid));
-        PKV_TRY(scan_range(r, mid, e));
+        PKV_TRY(scan_range(r, b, mid, true, false, false));
+        PKV_TRY(scan_range(r, mid, e, true, false, false));
     }
     return PKV_OK;
+}
+
+// The int8 kernels that re-read and re-select thresholds in-kernel: pkv_scan_tc.cu (<= 128 queries) and
+// pkv_scan_ts.cu (more); the 2-CTA shared-memory kernel (tc_ts = 0) does not.
+static bool live_int8_ok(const Index &ix, int nq) {
+    if (nq <= 128) return true;
+    return ix.opt.tc_ts && ix.dim_pad <= 1024 && (ix.sm_count % 2) == 0;
 }
 
 // Queries already on the device in caller layout; outputs to device buffers.
@@ -271,6 +318,14 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     r.use_tc = scan_tc_supported(ix, nq);
     r.use_tc_f32 = scan_tc_f32_supported(ix, nq);
     if (r.use_tc_f32) r.fs = filter_spec_tc_f32(ix, p.metric, nq);
+    r.d_ids = d_ids;
+    r.d_dist = d_dist;
+    r.d_counts = d_counts;
+    // Live mode (one launch over every row behind the bootstrap chunk, thresholds maintained in-kernel): the
+    // int8-image filter of f32 / f16 indexes and the int8 tensor-core kernels.  k <= 128: live_refresh keeps the
+    // <= k + refresh_every keys that can matter in 16 registers per lane.
+    const bool live_kernel = r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) == 8 : (r.use_tc && live_int8_ok(ix, nq));
+    r.live_capable = ix.opt.live && live_kernel && k <= 128 && N > r.safe_rows;
     ScanArgs &a = r.args;
     a.data = ix.d_data;
     a.pitch_bytes = ix.pitch;
@@ -290,6 +345,16 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     a.topk.cap = (uint32_t)ws.cap;
     a.topk.bitmap = d_bitmap;
     a.topk.bitmap_stride = p.bitmap_stride_words;
+    a.topk.live = 0;
+    a.topk.k = k;
+    {
+        int every = ix.opt.live_refresh > 0 ? ix.opt.live_refresh : 64;
+        if (every > k / 2 + 1) every = k / 2 + 1;  // a shallow search wants its few candidates to count at once
+        if (every < 4) every = 4;
+        a.topk.refresh_every = (uint32_t)every;
+    }
+    a.topk.fs = r.fs;
+    a.topk.q_mag_f = ws.d_q_mag_f;
 
     // Chunk schedule: the first chunk (no threshold yet: every row is a candidate) is sized
     // so it cannot overflow; afterwards a chunk of c rows behind `seen` scanned rows yields
@@ -306,20 +371,37 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // Optimistic mode: once every query has a threshold (after the first chunk) the remaining chunks
     // and their selects are enqueued back to back with no host round trip; the sticky overflow flag
     // is checked once at the end and, if it ever fired, the search is redone with a sync per chunk
-    // (which is what splits overflowing ranges).  Bitmap searches stay careful: their candidate
-    // rate is unknown until the first members are seen.
+    // (which is what splits overflowing ranges).  Bitmap searches stay careful until every query has a
+    // threshold: their candidate rate is unknown until the first members are seen.
     static const bool trace_env = getenv("PKV_TRACE") != nullptr;
     bool optimistic = ix.opt.optimistic && !d_bitmap && !trace_env;
+    bool allow_live = r.live_capable;
 restart:
     int64_t pos = 0;
     r.min_filled = 0;
+    r.last_max_raw = 0;
     r.unsynced = 0;
+    r.outputs_written = false;
+    int64_t prev_chunk = 0;
     while (pos < N) {
+        const bool filled = r.min_filled >= (uint32_t)k;
+        const bool go_live = allow_live && filled && pos > 0;
         int64_t chunk;
-        if (r.min_filled < (uint32_t)k) {
+        if (go_live) {
+            chunk = N - pos;
+        } else if (!filled) {
             chunk = r.safe_rows;
             if (pos == 0 && ix.opt.first_chunk_rows > 0 && ix.opt.first_chunk_rows < chunk)
                 chunk = ix.opt.first_chunk_rows;
+            // membership bitmap: a threshold-less chunk of c rows pushes (density * c) candidates per query; size the
+            // next one from the rate the last one showed (halved: the density may vary) instead of crawling in
+            // 4k-row steps through a sparse context - an overflow still splits the range
+            if (d_bitmap && pos > 0 && prev_chunk > 0) {
+                const double seen = r.last_max_raw > 0 ? (double)r.last_max_raw : 0.5;
+                double c = 0.5 * (double)r.safe_rows * (double)prev_chunk / seen;
+                if (c > 8.0 * (double)prev_chunk) c = 8.0 * (double)prev_chunk;
+                if (c > (double)chunk) chunk = (int64_t)c;
+            }
         } else {
             chunk = (int64_t)((double)pos * growth);
             if (chunk < r.safe_rows) chunk = r.safe_rows;
@@ -330,10 +412,11 @@ restart:
         // Every row of the threshold-less first chunk becomes a candidate of every query, so with >= k rows each
         // query has its k-th best afterwards: no host round trip is needed to learn that.  (If that ever failed
         // the thresholds would stay +inf, the next chunk would overflow, and the sticky flag redoes the search.)
-        const bool first_fill = optimistic && pos == 0 && r.min_filled < (uint32_t)k && chunk >= k;
-        const bool sync = !(optimistic && (first_fill || (r.min_filled >= (uint32_t)k && pos > 0)));
-        PKV_TRY(scan_range(r, pos, pos + chunk, sync));
+        const bool first_fill = optimistic && pos == 0 && !filled && chunk >= k;
+        const bool sync = !(optimistic && (first_fill || (filled && pos > 0)));
+        PKV_TRY(scan_range(r, pos, pos + chunk, sync, go_live, pos + chunk >= N));
         if (first_fill) r.min_filled = (uint32_t)k;
+        prev_chunk = chunk;
         pos += chunk;
     }
     if (r.unsynced > 0) {
@@ -347,19 +430,24 @@ restart:
             }
         }
         if (ws.h_status->sticky_overflow) {
+            // a candidate buffer overflowed somewhere along the unsynced chunks: redo the search on the careful
+            // schedule (a sync per chunk, overflowing ranges split, thresholds fixed per launch)
             r.depth_overflows++;
             optimistic = false;
+            allow_live = false;
             PKV_TRY(launch_reset_state(ws, nq, s));
             goto restart;
         }
     }
-    PKV_TRY(launch_finalize(ix, ws, nq, k, d_ids, d_dist, d_counts, s));
-    r.launches += 1;
+    if (!r.outputs_written) {
+        PKV_TRY(launch_finalize(ix, ws, nq, k, d_ids, d_dist, d_counts, s));
+        r.launches += 1;
+    }
     ix.n_launches += r.launches;
     ix.n_scan_launches += r.scan_launches;
     ix.n_fallback += r.depth_overflows;
-    ix.last_scan_ms += r.scan_ms;
-    ix.last_scan_kind = r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
+    g_last.scan_ms += r.scan_ms;
+    g_last.kind = r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
     return PKV_OK;
 }
 
@@ -389,7 +477,7 @@ static int check_search_args(Index *ix, const void *queries, int nq, const pkv_s
 
 static int search_impl(Index &ix, const void *queries, bool host_io, int nq, const pkv_search_params &p,
                        int64_t *out_ids, float *out_dist, int32_t *out_counts, cudaStream_t user_stream) {
-    PKV_TRY(use_device(ix.device));
+    PKV_USE_DEVICE(ix.device);
     std::shared_lock<std::shared_mutex> lock(ix.mu);
     PKV_TRY(check_search_args(&ix, queries, nq, &p, out_ids, out_dist, out_counts));
     if (nq == 0) return PKV_OK;
@@ -398,14 +486,17 @@ static int search_impl(Index &ix, const void *queries, bool host_io, int nq, con
     Workspace *ws = nullptr;
     const int sub = nq < SUB_BATCH ? nq : SUB_BATCH;
     PKV_TRY(make_workspace(ix, nq, k, host_io ? (size_t)sub * k : 0, &ws));
-    cudaStream_t s = (!host_io && user_stream) ? user_stream : ws->stream;
+    // Host API: the workspace's own stream (the call is synchronous anyway).  Device API: the caller's stream, where
+    // NULL means the legacy default stream - the search is then ordered behind whatever produced the queries and
+    // the bitmap on stream 0 (torch's default stream), as pkv.h promises.
+    cudaStream_t s = host_io ? ws->stream : user_stream;
     struct Guard {
         Index &ix;
         Workspace *ws;
         ~Guard() { release_workspace(ix, ws); }
     } guard{ix, ws};
     const int64_t words_per_bitmap = (ix.sealed_rows + 63) / 64;
-    ix.last_scan_ms = 0;
+    g_last.scan_ms = 0;
     if (ix.opt.time_kernels) PKV_CUDA(cudaEventRecord(ws->ev[2], s));
     for (int q0 = 0; q0 < nq; q0 += SUB_BATCH) {
         const int n = nq - q0 < SUB_BATCH ? nq - q0 : SUB_BATCH;
@@ -459,7 +550,7 @@ static int search_impl(Index &ix, const void *queries, bool host_io, int nq, con
     if (ix.opt.time_kernels) {
         float ms = 0.f;
         PKV_CUDA(cudaEventElapsedTime(&ms, ws->ev[2], ws->ev[3]));
-        ix.last_total_ms = ms;
+        g_last.total_ms = ms;
     }
     ix.n_searches += 1;
     ix.n_queries += nq;
@@ -617,7 +708,7 @@ static int grow(Index &ix, int64_t need_rows, bool exact = false) {
 }
 
 static int append_impl(Index &ix, const void *rows, const int64_t *row_ids, int64_t n, bool device_src) {
-    PKV_TRY(use_device(ix.device));
+    PKV_USE_DEVICE(ix.device);
     if (n < 0) return fail(PKV_ERR_INVALID, "n must be >= 0");
     if (n == 0) return PKV_OK;
     if (!rows) return fail(PKV_ERR_INVALID, "rows must not be NULL");
@@ -697,7 +788,7 @@ int pkv_artifact_scale(const uint8_t *artifact, size_t len, float *scale) {
 }
 
 int pkv_blob_absmax_device(int device, const float *d_values, int64_t n, float *absmax, void *stream) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (n < 0 || (n > 0 && !d_values) || !absmax) return fail(PKV_ERR_INVALID, "bad arguments");
     float *d_out = nullptr;
     PKV_CUDA(cudaMalloc((void **)&d_out, sizeof(float)));
@@ -712,7 +803,7 @@ int pkv_blob_absmax_device(int device, const float *d_values, int64_t n, float *
 }
 
 int pkv_blob_absmax(int device, const float *values, int64_t n, float *absmax) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (n < 0 || (n > 0 && !values) || !absmax) return fail(PKV_ERR_INVALID, "bad arguments");
     float *d = nullptr;
     PKV_CUDA(cudaMalloc((void **)&d, sizeof(float) * (n > 0 ? n : 1)));
@@ -725,7 +816,7 @@ int pkv_blob_absmax(int device, const float *values, int64_t n, float *absmax) {
 
 int pkv_quantize_int8_device(int device, const float *d_values, int64_t n, float scale, int8_t *d_codes,
                              void *stream) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (n < 0 || (n > 0 && (!d_values || !d_codes))) return fail(PKV_ERR_INVALID, "bad arguments");
     if (!(scale > 0.0f) || !(scale <= 3.402823466e+38f))
         return fail(PKV_ERR_INVALID, "scale must be a positive finite f32");
@@ -735,7 +826,7 @@ int pkv_quantize_int8_device(int device, const float *d_values, int64_t n, float
 }
 
 int pkv_quantize_int8(int device, const float *values, int64_t n, float scale, int8_t *codes) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (n < 0 || (n > 0 && (!values || !codes))) return fail(PKV_ERR_INVALID, "bad arguments");
     if (n == 0) return PKV_OK;
     float *d = nullptr;
@@ -760,7 +851,7 @@ int pkv_index_create(int device, int dim, int dtype, pkv_index **out) {
     *out = nullptr;
     if (dim < 1 || dim > 4096) return fail(PKV_ERR_INVALID, "dim %d out of range (1..4096)", dim);
     if (dtype != PKV_F32 && dtype != PKV_I8 && dtype != PKV_F16) return fail(PKV_ERR_INVALID, "unknown dtype %d", dtype);
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     cudaDeviceProp prop;
     PKV_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -784,7 +875,8 @@ int pkv_index_create(int device, int dim, int dtype, pkv_index **out) {
 int pkv_index_destroy(pkv_index *h) {
     if (!h) return PKV_OK;
     Index *ix = reinterpret_cast<Index *>(h);
-    cudaSetDevice(ix->device);
+    DeviceGuard guard;
+    if (guard.use(ix->device) != PKV_OK) return PKV_ERR_CUDA;
     for (Workspace *ws : ix->ws_free) delete ws;
     cudaFree(ix->d_data);
     cudaFree(ix->d_ids);
@@ -800,7 +892,7 @@ int pkv_index_destroy(pkv_index *h) {
 int pkv_index_reserve(pkv_index *h, int64_t rows) {
     if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
     Index &ix = *reinterpret_cast<Index *>(h);
-    PKV_TRY(use_device(ix.device));
+    PKV_USE_DEVICE(ix.device);
     if (rows < 0) return fail(PKV_ERR_INVALID, "rows must be >= 0");
     std::unique_lock<std::shared_mutex> lock(ix.mu);
     if (rows <= ix.cap_rows) return PKV_OK;
@@ -841,7 +933,7 @@ int pkv_index_set_row_base(pkv_index *h, int64_t row_base) {
 int pkv_index_seal(pkv_index *h) {
     if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
     Index &ix = *reinterpret_cast<Index *>(h);
-    PKV_TRY(use_device(ix.device));
+    PKV_USE_DEVICE(ix.device);
     std::unique_lock<std::shared_mutex> lock(ix.mu);
     if (ix.sealed_rows < ix.rows) {
         PKV_TRY(launch_row_mags(ix, ix.sealed_rows, ix.rows, nullptr));
@@ -919,7 +1011,7 @@ int pkv_distances_device(pkv_index *h, const void *d_queries, int nq, int metric
                          void *stream) {
     if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
     Index &ix = *reinterpret_cast<Index *>(h);
-    PKV_TRY(use_device(ix.device));
+    PKV_USE_DEVICE(ix.device);
     std::shared_lock<std::shared_mutex> lock(ix.mu);
     pkv_search_params p;
     memset(&p, 0, sizeof(p));
@@ -937,7 +1029,7 @@ int pkv_distances_device(pkv_index *h, const void *d_queries, int nq, int metric
         Workspace *ws;
         ~Guard() { release_workspace(ix, ws); }
     } guard{ix, ws};
-    cudaStream_t s = stream ? (cudaStream_t)stream : ws->stream;
+    cudaStream_t s = (cudaStream_t)stream;  // NULL: the legacy default stream (ordered behind the caller's stream-0 work)
     PKV_TRY(launch_prep_queries(ix, *ws, d_queries, nq, query_dtype, s));
     ScanArgs a{};
     a.data = ix.d_data;
@@ -967,7 +1059,7 @@ int pkv_rank_groups_device(pkv_index *h, const void *d_queries, int nq, const pk
     if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
     if (!p) return fail(PKV_ERR_INVALID, "rank params are NULL");
     Index &ix = *reinterpret_cast<Index *>(h);
-    PKV_TRY(use_device(ix.device));
+    PKV_USE_DEVICE(ix.device);
     if (nq < 1) return fail(PKV_ERR_INVALID, "nq must be >= 1");
     if (p->limit < 1 || p->offset < 0 || p->offset + p->limit > 2048)
         return fail(PKV_ERR_INVALID, "need limit >= 1, offset >= 0 and offset + limit <= 2048");
@@ -980,7 +1072,6 @@ int pkv_rank_groups_device(pkv_index *h, const void *d_queries, int nq, const pk
     cudaStream_t s = (cudaStream_t)stream;
     float *d_dist = nullptr;
     PKV_CUDA(cudaMallocAsync((void **)&d_dist, sizeof(float) * (size_t)(rows > 0 ? rows : 1) * nq, s));
-    if (!s) PKV_CUDA(cudaStreamSynchronize(s));  // the scoring pass below runs on a workspace stream
     int st = rows > 0 ? pkv_distances_device(h, d_queries, nq, p->metric, p->query_dtype, d_dist, stream) : PKV_OK;
     if (st == PKV_OK)
         st = rank_groups(d_dist, rows, nq, p->d_group_of_row, p->d_weights, p->n_groups, p->aggregation, p->offset,
@@ -994,7 +1085,7 @@ int pkv_rank_groups_device(pkv_index *h, const void *d_queries, int nq, const pk
 int pkv_index_get_rows_device(pkv_index *h, const int64_t *d_rows, int n, void *d_out, void *stream) {
     if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
     Index &ix = *reinterpret_cast<Index *>(h);
-    PKV_TRY(use_device(ix.device));
+    PKV_USE_DEVICE(ix.device);
     if (n < 0 || (n > 0 && (!d_rows || !d_out))) return fail(PKV_ERR_INVALID, "bad arguments");
     std::shared_lock<std::shared_mutex> lock(ix.mu);
     PKV_TRY(launch_gather_rows(ix, d_rows, n, d_out, (cudaStream_t)stream));
@@ -1004,7 +1095,7 @@ int pkv_index_get_rows_device(pkv_index *h, const int64_t *d_rows, int n, void *
 
 int pkv_merge_topk_device(int device, const int64_t *d_ids, const float *d_dist, int parts, int nq, int k,
                           int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts, void *stream) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (parts < 1 || parts > 256 || nq < 0 || k < 1) return fail(PKV_ERR_INVALID, "bad merge shape");
     if (nq > 0 && (!d_ids || !d_dist || !d_out_ids || !d_out_dist || !d_out_counts))
         return fail(PKV_ERR_INVALID, "NULL buffer");
@@ -1014,7 +1105,7 @@ int pkv_merge_topk_device(int device, const int64_t *d_ids, const float *d_dist,
 }
 
 int pkv_pack_topk_device(int device, const int64_t *d_ids, const float *d_dist, int64_t n, void *d_packed, void *stream) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (n < 0) return fail(PKV_ERR_INVALID, "n must be >= 0");
     if (n > 0 && (!d_ids || !d_dist || !d_packed)) return fail(PKV_ERR_INVALID, "NULL buffer");
     return launch_pack_topk(d_ids, d_dist, n, d_packed, (cudaStream_t)stream);
@@ -1022,7 +1113,7 @@ int pkv_pack_topk_device(int device, const int64_t *d_ids, const float *d_dist, 
 
 int pkv_merge_packed_device(int device, const void *d_packed, int parts, int nq, int k, int64_t *d_out_ids,
                             float *d_out_dist, int32_t *d_out_counts, void *stream) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (parts < 1 || parts > 256 || nq < 0 || k < 1) return fail(PKV_ERR_INVALID, "bad merge shape");
     if (nq > 0 && (!d_packed || !d_out_ids || !d_out_dist || !d_out_counts)) return fail(PKV_ERR_INVALID, "NULL buffer");
     return launch_merge_packed(d_packed, parts, nq, k, d_out_ids, d_out_dist, d_out_counts, (cudaStream_t)stream);
@@ -1030,7 +1121,7 @@ int pkv_merge_packed_device(int device, const void *d_packed, int parts, int nq,
 
 int pkv_aggregate_device(int device, const float *d_dist, const int64_t *d_item_of_row, const float *d_weights,
                          int64_t n, int64_t n_items, int agg, double *d_out, void *stream) {
-    PKV_TRY(use_device(device));
+    PKV_USE_DEVICE(device);
     if (n < 0 || n_items < 0 || agg < 0 || agg > 2) return fail(PKV_ERR_INVALID, "bad aggregate arguments");
     if ((n > 0 && (!d_dist || !d_item_of_row)) || (n_items > 0 && !d_out)) return fail(PKV_ERR_INVALID, "NULL buffer");
     PKV_TRY(launch_aggregate(d_dist, d_item_of_row, d_weights, n, n_items, agg, d_out, (cudaStream_t)stream));
@@ -1048,9 +1139,9 @@ int pkv_index_counters(pkv_index *h, pkv_counters *out) {
     out->scan_launches = ix.n_scan_launches;
     out->fallback_queries = ix.n_fallback;
     out->combined_searches = ix.n_combined;
-    out->last_scan_ms = ix.last_scan_ms;
-    out->last_total_ms = ix.last_total_ms;
-    out->last_scan_kind = ix.last_scan_kind;
+    out->last_scan_ms = g_last.scan_ms;
+    out->last_total_ms = g_last.total_ms;
+    out->last_scan_kind = g_last.kind;
     return PKV_OK;
 }
 
@@ -1080,6 +1171,9 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "combine")) ix.opt.combine = (int)value;
     else if (!strcmp(name, "tc_min_queries_f32")) ix.opt.tc_min_queries_f32 = (int)value;
     else if (!strcmp(name, "tc_min_queries_img")) ix.opt.tc_min_queries_img = (int)value;
+    else if (!strcmp(name, "live")) ix.opt.live = (int)value;
+    else if (!strcmp(name, "live_refresh")) ix.opt.live_refresh = (int)value;
+    else if (!strcmp(name, "img8_fused")) ix.opt.img8_fused = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;
 }

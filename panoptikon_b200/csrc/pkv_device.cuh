@@ -76,12 +76,156 @@ __device__ __forceinline__ bool topk_member(const TopkDev &t, int q, uint32_t ro
     return (__ldg(bm + (row >> 6)) >> (row & 63)) & 1ull;
 }
 
+// ---- live search state: per-query thresholds that other CTAs tighten while a scan runs ----------
+// Reads that must see those updates go to L2 (relaxed, gpu scope) instead of the non-coherent path.
+__device__ __forceinline__ uint64_t ld_live_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_live_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_live_f32(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+// *addr = min(*addr, v) for floats of either sign (never NaN): non-negative floats order like signed
+// ints, negative ones like reversed unsigned ints.
+__device__ __forceinline__ void atomic_min_f32(float *addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// Exact k-th best distance d_k -> the cheap threshold a scan kernel compares its own per-pair figure
+// against (FilterKind, pkv_internal.cuh).  Monotone in d_k; rounds towards "keep".
+__device__ __forceinline__ float filter_threshold(FilterSpec fs, float d_k, float b_mag) {
+    const float INF = __int_as_float(0x7f800000);
+    if (d_k != d_k) return INF;
+    if (fs.kind == FK_EXACT_DIST) return d_k;
+    if (fs.kind == FK_COS_RATIO) {
+        // in top-k only if dot/(sqrt(a)sqrt(b)) >= 1 - d_k - delta, delta covering the f32 rounding of d
+        double sb = sqrt((double)b_mag);
+        double T = (1.0 - (double)d_k - 2.4e-7) * sb;
+        double tf = -T + fabs(T) * (double)fs.rel + (double)fs.abs * sb + 1e-30;
+        float f = (float)tf;
+        if ((double)f < tf) f = nextafterf(f, INF);
+        return f;
+    }
+    double tf = (double)d_k * (double)d_k * (1.0 + (double)fs.rel) + (double)fs.abs;
+    float f = (float)tf;
+    if ((double)f < tf) f = nextafterf(f, INF);
+    return f;
+}
+
 // Appends (dist,row) to query q's candidate buffer when it beats the current k-th best.
 __device__ __forceinline__ void topk_push(const TopkDev &t, int q, uint32_t row, float dist) {
     uint64_t key = pack_key(dist, row);
     if (key >= __ldg(t.thr_key + q)) return;
     uint32_t slot = atomicAdd(t.cnt + q, 1u);
     if (slot < t.cap) t.cand[(size_t)q * t.cap + slot] = key;
+}
+
+// The same against the LIVE threshold.  Returns true when this push is the query's refresh trigger:
+// the caller's warp then re-selects the threshold (live_refresh).
+__device__ __forceinline__ bool topk_push_live(const TopkDev &t, int q, uint32_t row, float dist) {
+    const uint64_t key = pack_key(dist, row);
+    if (key >= ld_live_u64(t.thr_key + q)) return false;
+    const uint32_t slot = atomicAdd(t.cnt + q, 1u);
+    if (slot >= t.cap) return false;  // overflow: the final select sees cnt > cap and the search is redone chunked
+    t.cand[(size_t)q * t.cap + slot] = key;
+    return ((slot + 1u) % t.refresh_every) == 0u;
+}
+
+// In-kernel threshold maintenance (whole warp, converged).  The candidate buffer of query q is
+// append-only during a live launch: slots [0, cnt) hold keys of real (row, distance) pairs that beat the
+// threshold of their time, or KEY_MAX where the push is still in flight.  The k-th smallest key of ANY
+// set of >= k distinct real pairs bounds the final k-th best from above, so the result may be published
+// with atomicMin whatever other warps do meanwhile.  Only keys <= the current threshold can be among the
+// k smallest; they are gathered into registers (<= R per lane, else the refresh is skipped: thresholds
+// only ever tighten, a skipped refresh costs candidates, never correctness) and the k-th is found by
+// bisection on the distance bits, then on the row bits among the ties.
+template <int R>
+__device__ __noinline__ void live_refresh(const TopkDev &t, int q, int lane) {
+    const uint32_t raw = ld_live_u32(t.cnt + q);
+    const uint32_t n = raw < t.cap ? raw : t.cap;
+    const uint64_t told = ld_live_u64(t.thr_key + q);
+    const uint64_t *mine = t.cand + (size_t)q * t.cap;
+    uint32_t hi_w[R], lo_w[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        hi_w[j] = 0xFFFFFFFFu;
+        lo_w[j] = 0xFFFFFFFFu;
+    }
+    int c = 0;
+    for (uint32_t base = 0; base < n; base += 256) {
+        uint64_t kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {  // eight independent L2 reads in flight per lane
+            const uint32_t i = base + u * 32 + lane;
+            kk[u] = i < n ? ld_live_u64(mine + i) : KEY_MAX;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (kk[u] <= told && kk[u] != KEY_MAX) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    if (j == c) {
+                        hi_w[j] = (uint32_t)(kk[u] >> 32);
+                        lo_w[j] = (uint32_t)kk[u];
+                    }
+                }
+                ++c;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, c > R)) return;
+    const int total = __reduce_add_sync(0xffffffffu, c);
+    if (total < t.k) return;
+    // k-th smallest distance word: smallest v with count(hi <= v) >= k
+    uint32_t lo = 0u, hi = (uint32_t)(told >> 32);
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int cl = 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) cl += (j < c && hi_w[j] <= mid) ? 1 : 0;
+        if (__reduce_add_sync(0xffffffffu, cl) >= t.k) hi = mid;
+        else lo = mid + 1u;
+    }
+    const uint32_t dk = lo;
+    int less = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) less += (j < c && hi_w[j] < dk) ? 1 : 0;
+    const int need = t.k - __reduce_add_sync(0xffffffffu, less);  // >= 1: rank of the k-th among the ties at dk
+    uint32_t rlo = 0u, rhi = 0xFFFFFFFFu;
+    while (rlo < rhi) {
+        const uint32_t mid = rlo + ((rhi - rlo) >> 1);
+        int cl = 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) cl += (j < c && hi_w[j] == dk && lo_w[j] <= mid) ? 1 : 0;
+        if (__reduce_add_sync(0xffffffffu, cl) >= need) rhi = mid;
+        else rlo = mid + 1u;
+    }
+    const uint64_t kth = ((uint64_t)dk << 32) | (uint64_t)rlo;
+    if (lane == 0 && kth < told) {
+        atomicMin(reinterpret_cast<unsigned long long *>(t.thr_key + q), (unsigned long long)kth);
+        atomic_min_f32(t.thr_f + q, filter_threshold(t.fs, unordered_bits(dk), __ldg(t.q_mag_f + q)));
+    }
+}
+
+// Runs live_refresh for every lane whose last push was a trigger (q >= 0), one query at a time.
+template <int R>
+__device__ __forceinline__ void live_refresh_pending(const TopkDev &t, int trig_q, int lane) {
+    unsigned need = __ballot_sync(0xffffffffu, trig_q >= 0);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        const int qq = __shfl_sync(0xffffffffu, trig_q, src);
+        live_refresh<R>(t, qq, lane);
+        need &= need - 1u;
+    }
 }
 
 // ---- warp transpose-reduction --------------------------------------------

@@ -48,6 +48,12 @@ int fail(int code, const char *fmt, ...);
         if (_s != PKV_OK) return _s;  \
     } while (0)
 
+struct DeviceGuard {  // pkv_api.cu
+    int prev = -1;
+    int use(int device);
+    ~DeviceGuard();
+};
+
 // ------------------------------------------------------------- key packing
 // Total order of the contract: ascending f32 distance, NaN last, ties by ascending row.
 // -0.0 is canonicalised to +0.0 so that equal distances really tie.
@@ -107,11 +113,19 @@ struct FilterSpec {
 struct TopkDev {
     uint64_t *cand;          // [nq][cap]
     uint32_t *cnt;           // [nq] raw number of pushes (may exceed cap: overflow)
-    const uint64_t *thr_key; // [nq] exact key of the current k-th best (KEY_MAX while < k found)
-    const float *thr_f;      // [nq] filter-domain threshold
+    uint64_t *thr_key;       // [nq] exact key of the current k-th best (KEY_MAX while < k found)
+    float *thr_f;            // [nq] filter-domain threshold
     uint32_t cap;
     const uint64_t *bitmap;  // optional membership bits over local rows
     int64_t bitmap_stride;   // words per query, 0 = shared
+    // ---- live mode: ONE launch scans every remaining row; the thresholds are re-read from
+    // global memory tile by tile and tightened in-kernel (live_refresh, pkv_device.cuh) while the scan runs.
+    // The candidate buffers are append-only during such a launch and hold KEY_MAX in every unwritten slot.
+    int live;                // 0: thresholds are fixed for the duration of a launch (chunked schedule)
+    int k;                   // retrieval depth (live_refresh selects the k-th best)
+    uint32_t refresh_every;  // a push whose count reaches a multiple of this re-selects the query's threshold
+    FilterSpec fs;           // exact k-th distance -> filter-domain threshold (filter_threshold)
+    const float *q_mag_f;    // [nq] |q|^2 (FK_COS_RATIO)
 };
 
 struct ScanArgs {
@@ -200,6 +214,9 @@ struct Options {
                                      // 2 = always two, 3 = three whenever possible (96-row tiles up to D = 896)
     int ts_chunks = 0;               // K-chunks (8 KB boxes) per stage: 0 = auto (3 when they divide the row, else 2)
     int tc_min_queries = 1;          // int8: the TMA/tcgen05 kernel streams at ~95% of HBM peak even for one query
+    int live = 1;                    // one launch over all rows behind the bootstrap chunk, thresholds maintained in-kernel
+    int live_refresh = 64;           // pushes per query between two in-kernel threshold selections
+    int img8_fused = 1;              // int8-image path: exact re-scoring by warps of the scan kernel itself (no pend lists)
 };
 
 // Concurrent small searches (the server issues one query per request thread, 16 pool threads:
@@ -256,8 +273,6 @@ struct Index {
     std::atomic<int64_t> n_combined{0};  // searches that shared a scan with another caller
     // counters
     std::atomic<int64_t> n_searches{0}, n_queries{0}, n_launches{0}, n_scan_launches{0}, n_fallback{0};
-    double last_scan_ms = 0, last_total_ms = 0;
-    int last_scan_kind = 0;
 };
 
 // rows awaiting exact re-scoring (filter kernels of the floating-point paths)
@@ -294,7 +309,8 @@ int launch_gather_rows(const Index &ix, const int64_t *d_rows, int n, void *d_ou
 int launch_reset_status(Workspace &ws, cudaStream_t s);
 int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);
 int launch_reset_state(Workspace &ws, int nq, cudaStream_t s);
-int launch_select(const Index &ix, Workspace &ws, int nq, int k, int metric, FilterSpec fs, cudaStream_t s);
+int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, int64_t *d_ids,
+                  float *d_dist, int32_t *d_counts, cudaStream_t s);
 int launch_finalize(const Index &ix, Workspace &ws, int nq, int k, int64_t *d_ids, float *d_dist, int32_t *d_counts,
                     cudaStream_t s);
 int launch_row_mags(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);

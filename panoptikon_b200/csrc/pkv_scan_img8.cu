@@ -39,18 +39,24 @@ constexpr int CHUNK_BYTES = 128;
 constexpr int MAX_STAGES = 26;
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int IMG_THREADS = 64 + EPI_THREADS;
+constexpr int RS_WARPS = 6;  // exact re-scoring warps (fused mode): consume the survivors of this CTA's epilogue
+constexpr int RS_WARP0 = 2 + EPI_WARPS;
+constexpr int IMG_THREADS = 64 + EPI_THREADS + RS_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int HOLD_CAP = 64;
 constexpr int HOLD_FLUSH = 32;
 constexpr float BOUND_CLAMP = 1.07e9f;
+constexpr uint32_t RING_CAP = 1024;  // filter survivors in flight between the epilogue and the re-scoring warps
+constexpr uint32_t RING_MASK = RING_CAP - 1;
 
 struct ImgArgs {
     const float4 *row_meta;  // [rows] {|a|/s_a, |c|, |a - s_a c|/s_a, 1/s_a}
     const int8_t *q8;        // [nq][dim_pad8] query codes
     const float4 *q_meta;    // [nq] {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2}
-    PendDev pend;
+    PendDev pend;            // unfused mode: survivors parked for rescore_kernel
     int dim_pad8;
+    int fused;               // survivors are re-scored by this kernel's own warps (no pend lists, no second launch)
+    int rows_f16;            // stored rows are fp16 (f16 index), else f32
 };
 
 struct ImgShared {
@@ -59,13 +65,20 @@ struct ImgShared {
     uint64_t tmem_full[3];
     uint64_t tmem_empty[3];
     uint32_t tmem_base;
-    uint32_t pad;
+    uint32_t ring_head;  // tickets handed to producers (epilogue lanes)
+    uint32_t ring_tail;  // tickets handed to consumers (re-scoring warps)
+    uint32_t epi_done;   // epilogue warps that have pushed their last survivor
     uint32_t hold_cnt[EPI_WARPS];
-    alignas(16) float4 qc[QM_CTA];  // per query {c1, c2, ty, tz}
-    float qs[QM_CTA];               // per query: extra slack per unit of x2 (L2: rounding of |q|^2 and of the threshold)
+    alignas(16) float4 qm[QM_CTA];  // per query {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2} (fixed for the launch)
+    float thr[QM_CTA];              // per query: filter threshold (live mode: refreshed tile by tile)
     uint32_t hold_row[EPI_WARPS][HOLD_CAP];
     int hold_dot[EPI_WARPS][HOLD_CAP];
     uint32_t hold_col[EPI_WARPS][HOLD_CAP];
+    // bounded multi-producer multi-consumer ring (per-slot sequence numbers): slot i is writable by ticket t
+    // (t % RING_CAP == i) when seq[i] == t, readable when seq[i] == t + 1, and handed on with seq[i] = t + RING_CAP
+    uint32_t ring_seq[RING_CAP];
+    uint32_t ring_row[RING_CAP];
+    uint16_t ring_col[RING_CAP];
 };
 
 // Bound on acc below which a pair is certainly outside the top-k:   lead(row, query) - ty*v - tz*w - slack
@@ -105,20 +118,231 @@ __device__ __forceinline__ float pair_bound(const float4 qc, float qs, float x1l
     return lead - neg - (3e-5f * (mag + neg) + qs * x2hi + 4e-6f * qc.w * u + 1.0f);
 }
 
-// One pre-filter survivor: exact per-pair bound, membership, then park the row for exact re-scoring.
+// The threshold-dependent query constants of pair_bound from the fixed query figures qm and the filter threshold.
+template <int METRIC>
+__device__ __forceinline__ void query_consts(const float4 qm, float thr, float4 &qc, float &qs) {
+    if (METRIC == PKV_L2) {
+        qc.x = qm.x;
+        qc.y = 0.5f * (qm.w - thr);
+        qs = 1e-4f * 0.5f * qm.x * (qm.w + fabsf(thr));  // |q|^2 is a sequential f32 sum: good to ~6e-5
+    } else {
+        qc.x = -thr * qm.x;
+        qc.y = 0.f;
+        qs = 0.f;
+    }
+    qc.z = qm.y;
+    qc.w = qm.z;
+}
+
+__device__ __forceinline__ void ring_push(ImgShared *sh, uint32_t row, uint32_t col) {
+    const uint32_t t = atomicAdd(&sh->ring_head, 1u);
+    const uint32_t i = t & RING_MASK;
+    volatile uint32_t *seq = &sh->ring_seq[i];
+    while (*seq != t) __nanosleep(64);  // ring full: wait for the re-scoring warps (they never wait for us)
+    sh->ring_row[i] = row;
+    sh->ring_col[i] = (uint16_t)col;
+    __threadfence_block();
+    *seq = t + 1u;
+}
+
+// One pre-filter survivor: exact per-pair bound, membership, then hand the row on for exact re-scoring.
 template <int METRIC>
 __device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, int qbase, int col, int d, uint32_t row,
-                                          const ImgShared *sh) {
+                                          ImgShared *sh) {
     const int q = qbase + col;
     if (q >= a.nq || row >= a.row_end) return;
     const float4 m = __ldg(im.row_meta + row);
     float x1, x2;
     row_figures<METRIC>(m, x1, x2);
-    const float b = pair_bound<METRIC>(sh->qc[col], sh->qs[col], x1, x1, x2, x2, m.y, m.z, m.x);
+    float4 qc;
+    float qs;
+    query_consts<METRIC>(sh->qm[col], *(volatile const float *)&sh->thr[col], qc, qs);
+    const float b = pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x);
     if ((float)d < b) return;  // NaN bound (non-finite row or query): kept
     if (!topk_member(a.topk, q, row)) return;
+    if (im.fused) {
+        ring_push(sh, row, (uint32_t)col);
+        return;
+    }
     const uint32_t slot = atomicAdd(im.pend.cnt + q, 1u);
     if (slot < im.pend.cap) im.pend.rows[(size_t)q * im.pend.cap + slot] = row;
+}
+
+// ---- exact re-scoring inside the scan kernel (fused mode) -----------------------------------------
+// One warp, two (row, query) pairs at a time: twice the loads in flight per warp.  Same element order, same fmaf
+// chains and the same xor tree as rescore_kernel / the CUDA-core scan, so the reported score of a pair does not
+// depend on which kernel computed it.
+template <int METRIC>
+__device__ __forceinline__ void acc_f4(const float4 av, const float4 qv, float &acc, float &nrm) {
+    if (METRIC == PKV_L2) {
+        float t;
+        t = av.x - qv.x; acc = fmaf(t, t, acc);
+        t = av.y - qv.y; acc = fmaf(t, t, acc);
+        t = av.z - qv.z; acc = fmaf(t, t, acc);
+        t = av.w - qv.w; acc = fmaf(t, t, acc);
+    } else {
+        acc = fmaf(av.x, qv.x, acc);
+        acc = fmaf(av.y, qv.y, acc);
+        acc = fmaf(av.z, qv.z, acc);
+        acc = fmaf(av.w, qv.w, acc);
+    }
+    if (METRIC == PKV_COSINE) {
+        nrm = fmaf(av.x, av.x, nrm);
+        nrm = fmaf(av.y, av.y, nrm);
+        nrm = fmaf(av.z, av.z, nrm);
+        nrm = fmaf(av.w, av.w, nrm);
+    }
+}
+template <int METRIC>
+__device__ __forceinline__ void acc_h8(const uint4 raw8, const float4 q0v, const float4 q1v, float &acc, float &nrm) {
+    const __half2 *h = reinterpret_cast<const __half2 *>(&raw8);
+    float av[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 p = __half22float2(h[i]);
+        av[2 * i] = p.x;
+        av[2 * i + 1] = p.y;
+    }
+    const float qq[8] = {q0v.x, q0v.y, q0v.z, q0v.w, q1v.x, q1v.y, q1v.z, q1v.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (METRIC == PKV_L2) {
+            const float t = av[i] - qq[i];
+            acc = fmaf(t, t, acc);
+        } else {
+            acc = fmaf(av[i], qq[i], acc);
+        }
+    }
+    if (METRIC == PKV_COSINE) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nrm = fmaf(av[i], av[i], nrm);
+    }
+}
+
+template <int METRIC>
+__device__ __forceinline__ float exact_distance(float acc, float nrm, float qmag) {
+    if (METRIC == PKV_COSINE) return cosine_key((double)acc, (double)nrm, (double)qmag);
+    if (METRIC == PKV_L2) return l2_key_from_sum(acc);
+    return -acc;
+}
+
+template <int METRIC>
+__device__ __noinline__ void rescore_two(const ScanArgs &a, const ImgArgs &im, int qA, uint32_t rowA, bool haveB, int qB,
+                                         uint32_t rowB, int lane) {
+    const int nvec = a.dim_pad >> 2;  // float4 per padded f32 query
+    const uint8_t *rbA = (const uint8_t *)a.data + (size_t)rowA * (size_t)a.pitch_bytes;
+    const uint8_t *rbB = (const uint8_t *)a.data + (size_t)rowB * (size_t)a.pitch_bytes;
+    const float4 *qpA = (const float4 *)a.queries + (size_t)qA * nvec;
+    const float4 *qpB = (const float4 *)a.queries + (size_t)qB * nvec;
+    float accA = 0.f, nrmA = 0.f, accB = 0.f, nrmB = 0.f;
+    if (!im.rows_f16) {
+        const float4 *rpA = (const float4 *)rbA, *rpB = (const float4 *)rbB;
+#pragma unroll 2
+        for (int j = lane; j < nvec; j += 32) {
+            const float4 avA = ldg_stream_f4(rpA + j), avB = ldg_stream_f4(rpB + j);
+            const float4 qvA = __ldg(qpA + j), qvB = __ldg(qpB + j);
+            acc_f4<METRIC>(avA, qvA, accA, nrmA);
+            acc_f4<METRIC>(avB, qvB, accB, nrmB);
+        }
+    } else {
+        const uint4 *rpA = (const uint4 *)rbA, *rpB = (const uint4 *)rbB;
+        const int nvec8 = a.dim_pad >> 3;  // 8 halfs per lane per step, as scan_f16_simt_kernel
+#pragma unroll 2
+        for (int j = lane; j < nvec8; j += 32) {
+            const uint4 rA = __ldg(rpA + j), rB = __ldg(rpB + j);
+            acc_h8<METRIC>(rA, __ldg(qpA + 2 * j), __ldg(qpA + 2 * j + 1), accA, nrmA);
+            acc_h8<METRIC>(rB, __ldg(qpB + 2 * j), __ldg(qpB + 2 * j + 1), accB, nrmB);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        accA += __shfl_xor_sync(0xffffffffu, accA, o);
+        accB += __shfl_xor_sync(0xffffffffu, accB, o);
+        if (METRIC == PKV_COSINE) {
+            nrmA += __shfl_xor_sync(0xffffffffu, nrmA, o);
+            nrmB += __shfl_xor_sync(0xffffffffu, nrmB, o);
+        }
+    }
+    // lane 0 pushes pair A, lane 1 pair B
+    int trig_q = -1;
+    if (lane == 0 || (lane == 1 && haveB)) {
+        const int q = lane == 0 ? qA : qB;
+        const uint32_t row = lane == 0 ? rowA : rowB;
+        const float d = exact_distance<METRIC>(lane == 0 ? accA : accB, lane == 0 ? nrmA : nrmB, __ldg(a.q_mag_f + q));
+        if (a.topk.live) {
+            if (topk_push_live(a.topk, q, row, d)) trig_q = q;
+        } else {
+            topk_push(a.topk, q, row, d);
+        }
+    }
+    __syncwarp();
+    if (a.topk.live) live_refresh_pending<16>(a.topk, trig_q, lane);
+}
+
+// lane 0: is ring entry `t` published?  On success the payload is read and the slot handed back to the producers.
+__device__ __forceinline__ bool ring_take(ImgShared *sh, uint32_t t, uint32_t &row, uint32_t &col) {
+    const uint32_t i = t & RING_MASK;
+    volatile uint32_t *seq = &sh->ring_seq[i];
+    if (*seq != t + 1u) return false;
+    __threadfence_block();
+    row = *(volatile uint32_t *)&sh->ring_row[i];
+    col = *(volatile uint16_t *)&sh->ring_col[i];
+    __threadfence_block();
+    *seq = t + RING_CAP;
+    return true;
+}
+
+// Re-scoring warp: consumes ring entries until the CTA's epilogue warps are done and the ring is drained.
+template <int METRIC>
+__device__ __forceinline__ void rescore_loop(const ScanArgs &a, const ImgArgs &im, ImgShared *sh, int qbase,
+                                             uint32_t epi_expected, int lane) {
+    bool have_pending = false;
+    uint32_t pending_t = 0;
+    for (;;) {
+        // ---- entry A: own a ticket, wait until it is published (or can never be) ----
+        uint32_t rowA = 0, colA = 0, rowB = 0, colB = 0;
+        int state = 0;  // 0: drained, 1: A only, 2: A and B
+        if (lane == 0) {
+            const uint32_t tA = have_pending ? pending_t : atomicAdd(&sh->ring_tail, 1u);
+            have_pending = false;
+            for (;;) {
+                if (ring_take(sh, tA, rowA, colA)) {
+                    state = 1;
+                    break;
+                }
+                if (*(volatile uint32_t *)&sh->epi_done >= epi_expected) {
+                    // every producer has published its last entry: the head is final
+                    __threadfence_block();
+                    if ((int32_t)(tA - *(volatile uint32_t *)&sh->ring_head) >= 0) break;
+                    continue;  // the entry exists: take it on the next poll
+                }
+                __nanosleep(128);
+            }
+            // ---- entry B, only if one is already there (never wait for a partner while holding A) ----
+            if (state == 1 && (int32_t)(*(volatile uint32_t *)&sh->ring_head - *(volatile uint32_t *)&sh->ring_tail) > 0) {
+                const uint32_t tB = atomicAdd(&sh->ring_tail, 1u);
+                bool got = false;
+                for (int spin = 0; spin < 16 && !got; ++spin) got = ring_take(sh, tB, rowB, colB);
+                if (got) {
+                    state = 2;
+                } else {
+                    have_pending = true;  // still ours: becomes entry A of the next round
+                    pending_t = tB;
+                }
+            }
+        }
+        state = __shfl_sync(0xffffffffu, state, 0);
+        if (state == 0) break;
+        rowA = __shfl_sync(0xffffffffu, rowA, 0);
+        colA = __shfl_sync(0xffffffffu, colA, 0);
+        rowB = __shfl_sync(0xffffffffu, rowB, 0);
+        colB = __shfl_sync(0xffffffffu, colB, 0);
+        if (state == 1) {
+            rowB = rowA;
+            colB = colA;
+        }
+        rescore_two<METRIC>(a, im, qbase + (int)colA, rowA, state == 2, qbase + (int)colB, rowB, lane);
+    }
 }
 
 template <int METRIC>
@@ -194,9 +418,13 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             tc::mbar_init(&sh->tmem_empty[b], NCTA * EPI_USED);
         }
         for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
+        sh->ring_head = 0;
+        sh->ring_tail = 0;
+        sh->epi_done = 0;
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_rows);
     }
+    for (uint32_t i = threadIdx.x; i < RING_CAP; i += IMG_THREADS) sh->ring_seq[i] = i;
     if (warp == 1) {
         if (PAIR) {
             tc::tmem_alloc_cta2(&sh->tmem_base, TMEM_COLS);
@@ -211,31 +439,22 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
     tc::fence_after_sync();
     const uint32_t tmem_base = sh->tmem_base;
 
-    float4 qc = make_float4(0.f, 0.f, 0.f, 0.f);  // this thread's query (epilogue thread = one query)
-    float qs = 0.f;
-    bool live = false;  // padded query lanes keep nothing
-    if (warp >= 2) {
+    float4 qm = make_float4(0.f, 0.f, 0.f, 0.f);  // this thread's query (epilogue thread = one query)
+    float thr0 = 0.f;
+    bool real_q = false;  // padded query lanes keep nothing
+    if (warp >= 2 && warp < RS_WARP0) {
         const int ew = warp - 2, quarter = warp & 3;
         const int col = quarter * 32 + lane;
         const int q = qbase + col;
         if (q < a.nq) {
-            live = true;
-            const float thr = __ldg(a.topk.thr_f + q);  // +inf while the query has no threshold: keep everything
-            const float4 qm = __ldg(im.q_meta + q);
-            if (METRIC == PKV_L2) {
-                qc.x = qm.x;
-                qc.y = 0.5f * (qm.w - thr);
-                qs = 1e-4f * 0.5f * qm.x * (qm.w + fabsf(thr));  // |q|^2 is a sequential f32 sum: good to ~6e-5
-            } else {
-                qc.x = -thr * qm.x;
-                qc.y = 0.f;
-            }
-            qc.z = qm.y;
-            qc.w = qm.z;
+            real_q = true;
+            // +inf while the query has no threshold: keep everything
+            thr0 = a.topk.live ? ld_live_f32(a.topk.thr_f + q) : __ldg(a.topk.thr_f + q);
+            qm = __ldg(im.q_meta + q);
         }
         if ((ew >> 2) == 0) {
-            sh->qc[col] = qc;
-            sh->qs[col] = qs;
+            sh->qm[col] = qm;
+            sh->thr[col] = thr0;
         }
         // this CTA's 128 queries -> TMEM columns [0, dim_pad8/4): lane = query, 4 codes per column
         const int qrow = q < a.nq ? q : (a.nq - 1);
@@ -352,8 +571,20 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         bool row_ok = seq < ntiles && nrow < a.row_end;
         float4 m = row_ok ? __ldg(im.row_meta + nrow) : make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t empty0 = PAIR ? tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0) : tc::smem_u32(&sh->tmem_empty[0]);
+        // live mode: the query's threshold is re-read from global memory once per tile (the re-scoring warps of every
+        // CTA tighten it while the scan runs); the value for the next tile is fetched behind this tile's work
+        const bool live = a.topk.live != 0 && real_q;
+        float thr_next = thr0;
+        float4 qc;
+        float qs;
+        query_consts<METRIC>(qm, thr0, qc, qs);
         for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
+            if (live) {
+                query_consts<METRIC>(qm, thr_next, qc, qs);
+                if ((ew >> 2) == 0) *(volatile float *)&sh->thr[qcol] = thr_next;  // per-pair bound of consider_img
+                thr_next = ld_live_f32(a.topk.thr_f + qbase + qcol);
+            }
             // loosest figures over the warp's 32 rows (rows past the end must not loosen them)
             float x1, x2;
             row_figures<METRIC>(m, x1, x2);
@@ -369,7 +600,7 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             m = row_ok ? __ldg(im.row_meta + nrow) : make_float4(0.f, 0.f, 0.f, 0.f);
             float bf = pair_bound<METRIC>(qc, qs, x1lo, x1hi, x2lo, x2hi, vhi, whi, uhi);
             bf = fminf(fmaxf(bf, -BOUND_CLAMP), BOUND_CLAMP);  // NaN -> -clamp: keep everything
-            const int bound = live ? __float2int_rd(bf) : (int)BOUND_CLAMP;
+            const int bound = real_q ? __float2int_rd(bf) : (int)BOUND_CLAMP;
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();
             uint32_t v[32];
@@ -396,6 +627,14 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             flush_img<METRIC>(a, im, qbase, sh, ew, lane, HOLD_FLUSH);
         }
         flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
+        __syncwarp();
+        if (lane == 0) {  // this warp has published its last survivor
+            __threadfence_block();
+            atomicAdd(&sh->epi_done, 1u);
+        }
+    } else if (warp >= RS_WARP0) {
+        // ===================== exact re-scoring of this CTA's filter survivors (fused mode) =====================
+        if (im.fused) rescore_loop<METRIC>(a, im, sh, qbase, seq < nseq ? (uint32_t)EPI_USED : 0u, lane);
     }
 
     tc::fence_before_sync();
@@ -689,6 +928,10 @@ int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStre
     im.q_meta = ws.d_q8_meta;
     im.pend = PendDev{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap};
     im.dim_pad8 = ix.dim_pad8;
+    // live launches always re-score in-kernel: the thresholds can only move while the scan runs if the exact
+    // scores are produced while it runs
+    im.fused = (ix.opt.img8_fused || a.topk.live) ? 1 : 0;
+    im.rows_f16 = ix.dtype == PKV_F16 ? 1 : 0;
     // pend counters are zeroed by reset_state_kernel / select_kernel; the query codes are made once per search
     if (!ws.q8_ready) {
         img8_prep_queries_kernel<<<(a.nq + 7) / 8, 256, 0, s>>>((const float *)a.queries, a.nq, ix.dim, ix.dim_pad,
@@ -703,8 +946,10 @@ int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStre
         case PKV_L2: PKV_TRY(launch_img8_metric<PKV_L2>(ix, a, im, kchunks, s, launches)); break;
         default: PKV_TRY(launch_img8_metric<PKV_DOT>(ix, a, im, kchunks, s, launches)); break;
     }
-    PKV_TRY(launch_rescore(ix, a, im.pend, ws.d_status, s));
-    *launches += 1;
+    if (!im.fused) {
+        PKV_TRY(launch_rescore(ix, a, im.pend, ws.d_status, s));
+        *launches += 1;
+    }
     return PKV_OK;
 }
 

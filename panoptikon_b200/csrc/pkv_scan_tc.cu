@@ -57,17 +57,21 @@ struct TcShared {  // control block behind the data stages
 };
 
 // Exact filter, exact key, candidate push for one pre-filter survivor.
+// Returns the query whose threshold this push asks the warp to re-select (live mode), else -1.
 template <int METRIC>
-__device__ __noinline__ void consider(const ScanArgs &a, int q0, int col, int d, uint32_t row, const TcShared *sh) {
+__device__ __noinline__ int consider(const ScanArgs &a, int q0, int col, int d, uint32_t row, const TcShared *sh) {
     const int q = q0 + col;
-    if (q >= a.nq || row >= a.row_end) return;
+    if (q >= a.nq || row >= a.row_end) return -1;
     const int am = __ldg(a.row_mag_i + row);
     const int bm = sh->q_mag[col];
-    if (!exact_filter<METRIC>(d, am, bm, sh->thr[col])) return;
-    if (!topk_member(a.topk, q, row)) return;
+    if (!exact_filter<METRIC>(d, am, bm, *(volatile const float *)&sh->thr[col])) return -1;
+    if (!topk_member(a.topk, q, row)) return -1;
     const int8_t *rowp = (const int8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
     const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
-    topk_push(a.topk, q, row, i8_key(METRIC, d, am, bm, a.dim, rowp, qp));
+    const float key = i8_key(METRIC, d, am, bm, a.dim, rowp, qp);
+    if (a.topk.live) return topk_push_live(a.topk, q, row, key) ? q : -1;
+    topk_push(a.topk, q, row, key);
+    return -1;
 }
 
 // A lane found a pre-filter survivor: park it in its warp's shared-memory list (cheap) so that the
@@ -91,11 +95,15 @@ __device__ __forceinline__ void flush_held(const ScanArgs &a, int q0, TcShared *
     const uint32_t cnt = sh->hold_cnt[ew];
     if (cnt < min_cnt) return;
     const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
-    for (uint32_t e = lane; e < n; e += 32)
-        consider<METRIC>(a, q0, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+    int trig_q = -1;
+    for (uint32_t e = lane; e < n; e += 32) {
+        const int t = consider<METRIC>(a, q0, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+        if (t >= 0) trig_q = t;
+    }
     __syncwarp();
     if (lane == 0) sh->hold_cnt[ew] = 0;
     __syncwarp();
+    if (a.topk.live) live_refresh_pending<16>(a.topk, trig_q, lane);
 }
 
 template <int METRIC>
@@ -211,8 +219,18 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         uint32_t t = 0;
         uint32_t row = a.row_begin + blockIdx.x * TILE_M + quarter * 32 + lane;
         int am = (blockIdx.x < ntiles && row < a.row_end) ? __ldg(a.row_mag_i + row) : -1;
+        // live mode: warps 0..3 of the epilogue own one query each and re-read its threshold from global memory once
+        // per tile (other CTAs tighten it while the scan runs); a stale value in shared memory is only looser
+        const int lcol = ew * 32 + lane;
+        const bool live = a.topk.live != 0 && ew < 4 && (q0 + lcol) < a.nq;
+        float thr_next = live ? ld_live_f32(a.topk.thr_f + q0 + lcol) : 0.f;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
             const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            if (live) {
+                *(volatile float *)&sh->thr[lcol] = thr_next;
+                *(volatile float *)&sh->tq[lcol] = prefilter_query_figure<METRIC>(thr_next, sh->q_mag[lcol]);
+                thr_next = ld_live_f32(a.topk.thr_f + q0 + lcol);
+            }
             const uint32_t cur_row = row;
             const bool row_ok = am >= 0;
             // rows past the end must not loosen (min) the warp's bound

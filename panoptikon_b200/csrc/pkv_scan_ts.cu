@@ -57,17 +57,21 @@ struct TsShared {
 };
 
 // Exact filter, exact key, candidate push for one pre-filter survivor (col = query within the CTA).
+// Returns the query whose threshold this push asks the warp to re-select (live mode), else -1.
 template <int METRIC>
-__device__ __noinline__ void consider_ts(const ScanArgs &a, int qbase, int col, int d, uint32_t row, const TsShared *sh) {
+__device__ __noinline__ int consider_ts(const ScanArgs &a, int qbase, int col, int d, uint32_t row, const TsShared *sh) {
     const int q = qbase + col;
-    if (q >= a.nq || row >= a.row_end) return;
+    if (q >= a.nq || row >= a.row_end) return -1;
     const int am = __ldg(a.row_mag_i + row);
     const int bm = sh->q_mag[col];
-    if (!exact_filter<METRIC>(d, am, bm, sh->thr[col])) return;
-    if (!topk_member(a.topk, q, row)) return;
+    if (!exact_filter<METRIC>(d, am, bm, *(volatile const float *)&sh->thr[col])) return -1;
+    if (!topk_member(a.topk, q, row)) return -1;
     const int8_t *rowp = (const int8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
     const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
-    topk_push(a.topk, q, row, i8_key(METRIC, d, am, bm, a.dim, rowp, qp));
+    const float key = i8_key(METRIC, d, am, bm, a.dim, rowp, qp);
+    if (a.topk.live) return topk_push_live(a.topk, q, row, key) ? q : -1;
+    topk_push(a.topk, q, row, key);
+    return -1;
 }
 
 template <int METRIC>
@@ -88,11 +92,15 @@ __device__ __forceinline__ void flush_ts(const ScanArgs &a, int qbase, TsShared 
     const uint32_t cnt = sh->hold_cnt[ew];
     if (cnt < min_cnt) return;
     const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
-    for (uint32_t e = lane; e < n; e += 32)
-        consider_ts<METRIC>(a, qbase, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+    int trig_q = -1;
+    for (uint32_t e = lane; e < n; e += 32) {
+        const int t = consider_ts<METRIC>(a, qbase, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+        if (t >= 0) trig_q = t;
+    }
     __syncwarp();
     if (lane == 0) sh->hold_cnt[ew] = 0;
     __syncwarp();
+    if (a.topk.live) live_refresh_pending<16>(a.topk, trig_q, lane);
 }
 
 // TN = corpus rows per tile (MMA N), NBUF = accumulator buffers in TMEM behind the query columns.  The round trip
@@ -265,6 +273,11 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
         uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
         int am = (seq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
         const uint32_t empty0 = tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0);
+        // live mode: this thread's query threshold is re-read from global memory once per tile (other CTAs tighten it
+        // while the scan runs); the value for the next tile is fetched behind this tile's work
+        const bool live = a.topk.live != 0 && (qbase + qcol) < a.nq;
+        const int bm_q = live ? sh->q_mag[qcol] : 0;
+        float thr_next = live ? ld_live_f32(a.topk.thr_f + qbase + qcol) : 0.f;
         for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
             const bool row_ok = am >= 0;
@@ -272,6 +285,11 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             const int am_max = __reduce_max_sync(0xffffffffu, row_ok ? am : 0);
             nrow = a.row_begin + (tile + nseq) * TILE_N + col0 + lane;
             am = (tile + nseq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
+            if (live) {
+                tq = prefilter_query_figure<METRIC>(thr_next, bm_q);
+                if ((ew >> 2) == 0) *(volatile float *)&sh->thr[qcol] = thr_next;  // exact filter of consider_ts
+                thr_next = ld_live_f32(a.topk.thr_f + qbase + qcol);
+            }
             const int bound = prefilter_bound<METRIC>(tq, sqrtf((float)am_min), sqrtf((float)am_max), (float)am_min);
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();

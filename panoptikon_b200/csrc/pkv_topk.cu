@@ -92,32 +92,17 @@ __global__ void reset_status_kernel(SearchStatus *st) {
     st->min_filled = 0xFFFFFFFFu;
 }
 
-__device__ __forceinline__ float filter_threshold(FilterSpec fs, float d_k, float b_mag) {
-    const float INF = __int_as_float(0x7f800000);
-    if (d_k != d_k) return INF;
-    if (fs.kind == FK_EXACT_DIST) return d_k;
-    if (fs.kind == FK_COS_RATIO) {
-        // in top-k only if dot/(sqrt(a)sqrt(b)) >= 1 - d_k - delta, delta covering the f32 rounding of d
-        double sb = sqrt((double)b_mag);
-        double T = (1.0 - (double)d_k - 2.4e-7) * sb;
-        double tf = -T + fabs(T) * (double)fs.rel + (double)fs.abs * sb + 1e-30;
-        float f = (float)tf;
-        if ((double)f < tf) f = nextafterf(f, INF);
-        return f;
-    }
-    double tf = (double)d_k * (double)d_k * (1.0 + (double)fs.rel) + (double)fs.abs;
-    float f = (float)tf;
-    if ((double)f < tf) f = nextafterf(f, INF);
-    return f;
-}
-
 // ----------------------------------------------------------------- select
 // One CTA per query.  Sorts the candidate buffer (bitonic, shared memory), drops duplicate
 // keys (a chunk re-scanned after an overflow pushes the same rows again), keeps the best k
 // in cand[0..k) sorted ascending, and publishes the new exact and filter thresholds.
+//   clear_tail: the next launch is a live scan (append-only buffer): every slot behind the kept keys becomes KEY_MAX.
+//   out_ids != NULL: this is the last select of the search; the result rows are written here too (no finalize launch).
 __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *cnt, uint64_t *thr_key, float *thr_f,
                                                      const float *q_mag_f, SearchStatus *status, uint32_t cap, int k,
-                                                     FilterSpec fs, uint32_t *pend_cnt) {
+                                                     FilterSpec fs, uint32_t *pend_cnt, int clear_tail,
+                                                     const int64_t *row_ids, int64_t row_base, int64_t *out_ids,
+                                                     float *out_dist, int32_t *out_counts) {
     extern __shared__ uint64_t s_keys[];
     __shared__ uint64_t s_kth;
     __shared__ int s_m;
@@ -185,6 +170,24 @@ __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *c
             atomicOr(&status->sticky_overflow, 1u);
         }
         atomicMin(&status->min_filled, m);
+    }
+    const uint32_t m_all = (uint32_t)s_m;
+    if (clear_tail)
+        for (uint32_t i = m_all + threadIdx.x; i < cap; i += blockDim.x) mine[i] = KEY_MAX;
+    if (out_ids) {
+        for (uint32_t i = threadIdx.x; i < (uint32_t)k; i += blockDim.x) {
+            int64_t id = -1;
+            float d = __int_as_float(0x7fc00000);
+            if (i < m_all) {
+                const uint64_t key = mine[i];
+                const uint32_t row = (uint32_t)key;
+                id = row_ids ? row_ids[row] : row_base + (int64_t)row;
+                d = unordered_bits((uint32_t)(key >> 32));
+            }
+            out_ids[(size_t)q * k + i] = id;
+            out_dist[(size_t)q * k + i] = d;
+        }
+        if (threadIdx.x == 0) out_counts[q] = (int32_t)m_all;
     }
 }
 
@@ -471,14 +474,14 @@ int launch_reset_status(Workspace &ws, cudaStream_t s) {
     return PKV_OK;
 }
 
-int launch_select(const Index &ix, Workspace &ws, int nq, int k, int metric, FilterSpec fs, cudaStream_t s) {
-    (void)ix;
-    (void)metric;
+int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, int64_t *d_ids,
+                  float *d_dist, int32_t *d_counts, cudaStream_t s) {
     if (nq <= 0) return PKV_OK;
     const size_t smem = (size_t)ws.cap * sizeof(uint64_t);
     PKV_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_kernel<<<nq, 512, smem, s>>>(ws.d_cand, ws.d_cnt, ws.d_thr_key, ws.d_thr_f, ws.d_q_mag_f, ws.d_status,
-                                        (uint32_t)ws.cap, k, fs, ws.d_pend_cnt);
+                                        (uint32_t)ws.cap, k, fs, ws.d_pend_cnt, clear_tail ? 1 : 0, ix.d_ids,
+                                        ix.row_base, d_ids, d_dist, d_counts);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }
