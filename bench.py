@@ -469,6 +469,11 @@ def main():
         "gpu_launches": int(c1.kernel_launches - c0.kernel_launches) + merge_launches[0],
         "roofline": roofline,
         "overflow_rescans": int(c1.fallback_queries - c0.fallback_queries),
+        # what the in-kernel machinery did per step (device counters of the searches in the timed region)
+        "search_stats": {"live_refreshes_per_step": (c1.live_refreshes - c0.live_refreshes) / a.steps,
+                         "live_refresh_skips_per_step": (c1.live_refresh_skips - c0.live_refresh_skips) / a.steps,
+                         "rescored_rows_per_query": (c1.rescored_pairs - c0.rescored_pairs) / a.steps / a.batch,
+                         "deferred_rows_per_query": (c1.deferred_pairs - c0.deferred_pairs) / a.steps / a.batch},
     }
 
     # ---- full-size properties of the last batch's result (the oracle cannot scan 10M rows in the time budget):

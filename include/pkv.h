@@ -245,6 +245,10 @@ typedef struct {
                                    8 tc-i8 on the int8 image of f32/f16 rows (pkv_scan_img8.cu) */
     int32_t reserved;
     int64_t combined_searches;  /* host searches that shared one corpus scan with concurrent callers */
+    int64_t live_refreshes;     /* in-kernel threshold selections (live mode) */
+    int64_t live_refresh_skips; /* ... that gave up because too many keys were still live */
+    int64_t rescored_pairs;     /* (row, query) pairs re-scored exactly inside the int8-image scan kernel */
+    int64_t deferred_pairs;     /* ... parked by a live launch and re-scored behind it, after the final-threshold check */
 } pkv_counters;
 int pkv_index_counters(pkv_index *h, pkv_counters *out);
 /* Tuning knobs for tests and the bench: "image_mask" (which filter images an f32/f16

@@ -45,6 +45,8 @@ class Counters(C.Structure):
         ("scan_launches", C.c_int64), ("fallback_queries", C.c_int64),
         ("last_scan_ms", C.c_double), ("last_total_ms", C.c_double),
         ("last_scan_kind", C.c_int32), ("reserved", C.c_int32), ("combined_searches", C.c_int64),
+        ("live_refreshes", C.c_int64), ("live_refresh_skips", C.c_int64), ("rescored_pairs", C.c_int64),
+        ("deferred_pairs", C.c_int64),
     ]
 
 

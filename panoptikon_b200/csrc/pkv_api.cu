@@ -86,6 +86,9 @@ Workspace::~Workspace() {
     cudaFree(d_status);
     cudaFree(d_pend_rows);
     cudaFree(d_pend_cnt);
+    cudaFree(d_defer_rows);
+    cudaFree(d_defer_dots);
+    cudaFree(d_defer_cnt);
     cudaFree(d_q16);
     cudaFree(d_q8);
     cudaFree(d_q8_meta);
@@ -161,6 +164,9 @@ static int make_workspace(Index &ix, int nq, int k, size_t out_rows, Workspace *
             ws->pend_cap = 4 * cap;
             A((void **)&ws->d_pend_rows, sizeof(uint32_t) * (size_t)nq_cap * ws->pend_cap);
             A((void **)&ws->d_pend_cnt, sizeof(uint32_t) * nq_cap);
+            A((void **)&ws->d_defer_rows, sizeof(uint32_t) * (size_t)nq_cap * ws->pend_cap);
+            A((void **)&ws->d_defer_dots, sizeof(int) * (size_t)nq_cap * ws->pend_cap);
+            A((void **)&ws->d_defer_cnt, sizeof(uint32_t) * nq_cap);
             A((void **)&ws->d_q16, sizeof(__half) * (size_t)nq_cap * ix.dim_pad_h);
             A((void **)&ws->d_q_scale, sizeof(float) * nq_cap);
             A((void **)&ws->d_q8, (size_t)nq_cap * ix.dim_pad8);
@@ -210,6 +216,8 @@ struct SearchRun {
     float *d_dist = nullptr;
     int32_t *d_counts = nullptr;
     bool outputs_written = false;
+    bool defer = false;        // int8-image path: band pairs are parked until the final thresholds are known
+    bool defer_dirty = false;  // a scan has parked pairs since the last deferred pass
 };
 
 // One chunk: scan kernel(s) over rows [b, e), then the select.
@@ -246,13 +254,22 @@ static int scan_range(SearchRun &r, int64_t b, int64_t e, bool sync, bool live, 
         PKV_TRY(launch_scan_tc(r.ix, r.args, r.s, &n));
     else
         PKV_TRY(launch_scan_simt(r.ix, r.args, r.s, &n));
+    if (r.defer && r.use_tc_f32 && !bootstrap) r.defer_dirty = true;
+    bool deferred_now = false;
+    if (last && r.defer_dirty) {
+        // the pairs parked by every chunk of this search, against the thresholds the whole scan arrived at
+        PKV_TRY(launch_rescore_deferred(r.ix, r.args, r.ws, r.s));
+        n += 1;
+        r.defer_dirty = false;
+        deferred_now = true;
+    }
     r.launches += n;
     r.scan_launches += n;
     if (timed) PKV_CUDA(cudaEventRecord(ev_end, r.s));
     // a chunk that may be followed by a live launch leaves KEY_MAX behind the kept keys (append-only buffers)
     const bool write_out = last && !sync;  // a synced chunk may still be split and re-scanned
-    PKV_TRY(launch_select(r.ix, r.ws, r.nq, r.k, r.fs, /*clear_tail=*/r.live_capable && !last, write_out ? r.d_ids : nullptr,
-                          r.d_dist, r.d_counts, r.s));
+    PKV_TRY(launch_select(r.ix, r.ws, r.nq, r.k, r.fs, /*clear_tail=*/r.live_capable && !last, deferred_now,
+                          write_out ? r.d_ids : nullptr, r.d_dist, r.d_counts, r.s));
     if (write_out) r.outputs_written = true;
     r.launches += sync ? 2 : 1;
     if (!sync) {
@@ -325,7 +342,15 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // int8-image filter of f32 / f16 indexes and the int8 tensor-core kernels.  k <= 128: live_refresh keeps the
     // <= k + refresh_every keys that can matter in 16 registers per lane.
     const bool live_kernel = r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) == 8 : (r.use_tc && live_int8_ok(ix, nq));
-    r.live_capable = ix.opt.live && live_kernel && k <= 128 && N > r.safe_rows;
+    r.live_capable = ix.opt.live && live_kernel && k <= 128 && N > r.safe_rows &&
+                     !(r.use_tc_f32 && ix.opt.img8_fused == 0);
+    // The live launch starts behind a short chunked prefix: a threshold learnt from few rows passes so many pairs
+    // that the in-kernel feedback (re-score -> re-select -> re-read, ~10 us = tens of thousands of rows scanned
+    // meanwhile) cannot keep up; behind ~64k rows the pass rate is low enough for the lag not to matter.
+    const int64_t live_start = ix.opt.live_start_rows > 0 ? ix.opt.live_start_rows : 131072;
+    // Measured on B200 (profiles/README.md, round 2): the live launch has a start-up transient and a drain tail of
+    // ~0.4 ms that only a long scan amortises; below ~4M rows the chunked schedule with deferred band pairs is faster.
+    if (ix.opt.live == 1 && N - live_start < ix.opt.live_min_rows) r.live_capable = false;
     ScanArgs &a = r.args;
     a.data = ix.d_data;
     a.pitch_bytes = ix.pitch;
@@ -348,13 +373,17 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     a.topk.live = 0;
     a.topk.k = k;
     {
-        int every = ix.opt.live_refresh > 0 ? ix.opt.live_refresh : 64;
-        if (every > k / 2 + 1) every = k / 2 + 1;  // a shallow search wants its few candidates to count at once
+        int every = ix.opt.live_refresh > 0 ? ix.opt.live_refresh : 32;
+        if (every > k / 2 + 1 && ix.opt.live_refresh <= 0) every = k / 2 + 1;  // a shallow search wants its few candidates to count at once
         if (every < 4) every = 4;
         a.topk.refresh_every = (uint32_t)every;
     }
     a.topk.fs = r.fs;
     a.topk.q_mag_f = ws.d_q_mag_f;
+    a.topk.status = ws.d_status;
+    r.defer = r.use_tc_f32 && scan_tc_f32_kind(ix, nq) == 8 && ix.opt.img8_defer != 0;
+    if (!r.defer && r.use_tc_f32) r.live_capable = false;  // the live launch needs somewhere to park what it cannot take
+    a.topk.defer = r.defer ? 1 : 0;
 
     // Chunk schedule: the first chunk (no threshold yet: every row is a candidate) is sized
     // so it cannot overflow; afterwards a chunk of c rows behind `seen` scanned rows yields
@@ -365,7 +394,8 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     if (growth > 4.0 && nq >= 32) growth = 4.0;  // few queries: candidates are cheap, chunks are not
     // int8-image filter: its error band passes ~(growth - 1) * 4k rows per chunk to the re-scorer (3 KB each), so a
     // wide batch does better with fresher thresholds (more, smaller chunks): measured 1.5x best at 256..1024 queries
-    if (r.use_tc_f32 && scan_tc_f32_kind(ix, nq) == 8 && nq > 128 && growth > 1.5) growth = 1.5;
+    // (with the band pairs deferred to the end of the search the volume is ~3x smaller and 4x growth is best again)
+    if (r.use_tc_f32 && scan_tc_f32_kind(ix, nq) == 8 && nq > 128 && growth > 1.5 && !r.defer) growth = 1.5;
     if (ix.opt.chunk_growth_x100 > 0) growth = ix.opt.chunk_growth_x100 / 100.0;
     if (growth < 0.25) growth = 0.25;
     // Optimistic mode: once every query has a threshold (after the first chunk) the remaining chunks
@@ -382,15 +412,19 @@ restart:
     r.last_max_raw = 0;
     r.unsynced = 0;
     r.outputs_written = false;
+    r.defer_dirty = false;
     int64_t prev_chunk = 0;
     while (pos < N) {
         const bool filled = r.min_filled >= (uint32_t)k;
-        const bool go_live = allow_live && filled && pos > 0;
+        const bool go_live = allow_live && filled && pos >= live_start;
         int64_t chunk;
         if (go_live) {
             chunk = N - pos;
         } else if (!filled) {
             chunk = r.safe_rows;
+            // before a live launch a smaller bootstrap chunk pays: its dense scoring and its 4096-key sort are the
+            // largest fixed costs of a search
+            if (pos == 0 && (allow_live || r.defer) && !d_bitmap && chunk > 2048 && k <= 512) chunk = 2048;
             if (pos == 0 && ix.opt.first_chunk_rows > 0 && ix.opt.first_chunk_rows < chunk)
                 chunk = ix.opt.first_chunk_rows;
             // membership bitmap: a threshold-less chunk of c rows pushes (density * c) candidates per query; size the
@@ -403,10 +437,12 @@ restart:
                 if (c > (double)chunk) chunk = (int64_t)c;
             }
         } else {
-            chunk = (int64_t)((double)pos * growth);
+            // before a live launch the prefix grows 4x per chunk whatever the batch (few chunks, then one launch)
+            chunk = (int64_t)((double)pos * (allow_live ? 4.0 : growth));
             if (chunk < r.safe_rows) chunk = r.safe_rows;
+            if (allow_live && pos + chunk > live_start) chunk = live_start - pos > r.safe_rows ? live_start - pos : chunk;
         }
-        if (chunk >= 1024) chunk = chunk / 128 * 128;
+        if (chunk >= 1024 && !go_live) chunk = chunk / 128 * 128;
         if (chunk > N - pos) chunk = N - pos;
         if (chunk < 1) chunk = 1;
         // Every row of the threshold-less first chunk becomes a candidate of every query, so with >= k rows each
@@ -431,18 +467,47 @@ restart:
         }
         if (ws.h_status->sticky_overflow) {
             // a candidate buffer overflowed somewhere along the unsynced chunks: redo the search on the careful
-            // schedule (a sync per chunk, overflowing ranges split, thresholds fixed per launch)
+            // schedule (a sync per chunk, overflowing ranges split, thresholds fixed per launch, nothing deferred)
             r.depth_overflows++;
             optimistic = false;
             allow_live = false;
+            r.defer = false;
+            a.topk.defer = 0;
             PKV_TRY(launch_reset_state(ws, nq, s));
             goto restart;
+        }
+    }
+    if (r.defer && ws.h_status->defer_overflow) {
+        // a query parked more pairs than its list holds (status as of the last sync, which followed the deferred pass)
+        r.depth_overflows++;
+        optimistic = false;
+        allow_live = false;
+        r.defer = false;
+        a.topk.defer = 0;
+        PKV_TRY(launch_reset_state(ws, nq, s));
+        goto restart;
+    }
+    if (r.defer_dirty) {
+        // a split re-scan behind the last chunk parked pairs again: one more deferred pass and select
+        PKV_TRY(launch_rescore_deferred(ix, r.args, ws, s));
+        PKV_TRY(launch_select(ix, ws, nq, k, r.fs, false, true, nullptr, nullptr, nullptr, s));
+        r.defer_dirty = false;
+        r.launches += 2;
+        PKV_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(SearchStatus), cudaMemcpyDeviceToHost, s));
+        PKV_CUDA(cudaStreamSynchronize(s));
+        if (ws.h_status->sticky_overflow && !ws.h_status->any_overflow) {
+            // (cannot happen on the careful schedule: its ranges are split until nothing overflows)
         }
     }
     if (!r.outputs_written) {
         PKV_TRY(launch_finalize(ix, ws, nq, k, d_ids, d_dist, d_counts, s));
         r.launches += 1;
     }
+    // h_status holds the status as of the last host sync of this search (every path ends with one)
+    ix.n_live_refreshes += ws.h_status->live_refreshes;
+    ix.n_live_skips += ws.h_status->live_skips;
+    ix.n_rescored += ws.h_status->rescored;
+    ix.n_deferred += ws.h_status->deferred;
     ix.n_launches += r.launches;
     ix.n_scan_launches += r.scan_launches;
     ix.n_fallback += r.depth_overflows;
@@ -1139,6 +1204,10 @@ int pkv_index_counters(pkv_index *h, pkv_counters *out) {
     out->scan_launches = ix.n_scan_launches;
     out->fallback_queries = ix.n_fallback;
     out->combined_searches = ix.n_combined;
+    out->live_refreshes = ix.n_live_refreshes;
+    out->live_refresh_skips = ix.n_live_skips;
+    out->rescored_pairs = ix.n_rescored;
+    out->deferred_pairs = ix.n_deferred;
     out->last_scan_ms = g_last.scan_ms;
     out->last_total_ms = g_last.total_ms;
     out->last_scan_kind = g_last.kind;
@@ -1174,6 +1243,9 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "live")) ix.opt.live = (int)value;
     else if (!strcmp(name, "live_refresh")) ix.opt.live_refresh = (int)value;
     else if (!strcmp(name, "img8_fused")) ix.opt.img8_fused = (int)value;
+    else if (!strcmp(name, "img8_defer")) ix.opt.img8_defer = (int)value;
+    else if (!strcmp(name, "live_start_rows")) ix.opt.live_start_rows = value;
+    else if (!strcmp(name, "live_min_rows")) ix.opt.live_min_rows = value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;
 }

@@ -150,9 +150,16 @@ __device__ __forceinline__ bool topk_push_live(const TopkDev &t, int q, uint32_t
 // bisection on the distance bits, then on the row bits among the ties.
 template <int R>
 __device__ __noinline__ void live_refresh(const TopkDev &t, int q, int lane) {
-    const uint32_t raw = ld_live_u32(t.cnt + q);
+    // one lane reads the moving state: every loop below must run the same number of times in all lanes
+    uint32_t raw = 0;
+    uint64_t told = 0;
+    if (lane == 0) {
+        raw = ld_live_u32(t.cnt + q);
+        told = ld_live_u64(t.thr_key + q);
+    }
+    raw = __shfl_sync(0xffffffffu, raw, 0);
+    told = __shfl_sync(0xffffffffu, told, 0);
     const uint32_t n = raw < t.cap ? raw : t.cap;
-    const uint64_t told = ld_live_u64(t.thr_key + q);
     const uint64_t *mine = t.cand + (size_t)q * t.cap;
     uint32_t hi_w[R], lo_w[R];
 #pragma unroll
@@ -182,11 +189,18 @@ __device__ __noinline__ void live_refresh(const TopkDev &t, int q, int lane) {
             }
         }
     }
-    if (__any_sync(0xffffffffu, c > R)) return;
+    if (__any_sync(0xffffffffu, c > R)) {
+        if (lane == 0) atomicAdd(&t.status->live_skips, 1u);
+        return;
+    }
     const int total = __reduce_add_sync(0xffffffffu, c);
     if (total < t.k) return;
-    // k-th smallest distance word: smallest v with count(hi <= v) >= k
-    uint32_t lo = 0u, hi = (uint32_t)(told >> 32);
+    // k-th smallest distance word: smallest v with count(hi <= v) >= k.  The live keys span a narrow band of
+    // distances, so the bisection starts from their own range instead of [0, threshold]
+    uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < R; ++j) mn = (j < c && hi_w[j] < mn) ? hi_w[j] : mn;
+    uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = (uint32_t)(told >> 32);
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         int cl = 0;
@@ -196,20 +210,31 @@ __device__ __noinline__ void live_refresh(const TopkDev &t, int q, int lane) {
         else lo = mid + 1u;
     }
     const uint32_t dk = lo;
-    int less = 0;
+    int less = 0, ties = 0;
+    uint32_t tie_row = 0xFFFFFFFFu;
 #pragma unroll
-    for (int j = 0; j < R; ++j) less += (j < c && hi_w[j] < dk) ? 1 : 0;
-    const int need = t.k - __reduce_add_sync(0xffffffffu, less);  // >= 1: rank of the k-th among the ties at dk
-    uint32_t rlo = 0u, rhi = 0xFFFFFFFFu;
-    while (rlo < rhi) {
-        const uint32_t mid = rlo + ((rhi - rlo) >> 1);
-        int cl = 0;
+    for (int j = 0; j < R; ++j) {
+        less += (j < c && hi_w[j] < dk) ? 1 : 0;
+        if (j < c && hi_w[j] == dk) {
+            ++ties;
+            tie_row = lo_w[j] < tie_row ? lo_w[j] : tie_row;
+        }
+    }
+    const int need = t.k - __reduce_add_sync(0xffffffffu, less);  // >= 1: rank of the k-th among the keys at dk
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    uint32_t rlo = __reduce_min_sync(0xffffffffu, tie_row), rhi = 0xFFFFFFFFu;
+    if (ties > 1 && need > 1) {  // several rows share the k-th distance: bisect on the row word among them
+        while (rlo < rhi) {
+            const uint32_t mid = rlo + ((rhi - rlo) >> 1);
+            int cl = 0;
 #pragma unroll
-        for (int j = 0; j < R; ++j) cl += (j < c && hi_w[j] == dk && lo_w[j] <= mid) ? 1 : 0;
-        if (__reduce_add_sync(0xffffffffu, cl) >= need) rhi = mid;
-        else rlo = mid + 1u;
+            for (int j = 0; j < R; ++j) cl += (j < c && hi_w[j] == dk && lo_w[j] <= mid) ? 1 : 0;
+            if (__reduce_add_sync(0xffffffffu, cl) >= need) rhi = mid;
+            else rlo = mid + 1u;
+        }
     }
     const uint64_t kth = ((uint64_t)dk << 32) | (uint64_t)rlo;
+    if (lane == 0) atomicAdd(&t.status->live_refreshes, 1u);
     if (lane == 0 && kth < told) {
         atomicMin(reinterpret_cast<unsigned long long *>(t.thr_key + q), (unsigned long long)kth);
         atomic_min_f32(t.thr_f + q, filter_threshold(t.fs, unordered_bits(dk), __ldg(t.q_mag_f + q)));

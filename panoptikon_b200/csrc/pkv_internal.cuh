@@ -109,6 +109,20 @@ struct FilterSpec {
     float abs;  // absolute slack, in units of the filter figure (scaled by sqrt(bMag) for FK_COS_RATIO)
 };
 
+struct SearchStatus {  // device -> pinned host after every chunk
+    uint32_t max_raw_cnt;
+    uint32_t any_overflow;
+    uint32_t min_filled;
+    uint32_t sticky_overflow;  // like any_overflow but only cleared at the start of a search
+    // cumulative over one search (cleared with sticky_overflow): what the in-kernel machinery did
+    uint32_t live_refreshes;   // in-kernel threshold selections that ran to completion
+    uint32_t live_skips;       // ... that gave up (more live keys than the register file of a warp holds)
+    uint32_t rescored;         // (row, query) pairs re-scored exactly inside the int8-image scan kernel
+    uint32_t deferred;         // ... parked until the end of the search and re-scored after the final-threshold check
+    uint32_t defer_overflow;   // a query parked more pairs than its list holds: the search is redone without deferral
+    uint32_t reserved[3];
+};
+
 // ------------------------------------------------------------ device state
 struct TopkDev {
     uint64_t *cand;          // [nq][cap]
@@ -126,6 +140,8 @@ struct TopkDev {
     uint32_t refresh_every;  // a push whose count reaches a multiple of this re-selects the query's threshold
     FilterSpec fs;           // exact k-th distance -> filter-domain threshold (filter_threshold)
     const float *q_mag_f;    // [nq] |q|^2 (FK_COS_RATIO)
+    SearchStatus *status;    // device counters of the search
+    int defer;               // int8-image path: pairs inside the filter's error band are parked until the end of the search
 };
 
 struct ScanArgs {
@@ -146,12 +162,6 @@ struct ScanArgs {
     int64_t dense_stride;  // elements between consecutive queries in dense_out
 };
 
-struct SearchStatus {  // device -> pinned host after every chunk
-    uint32_t max_raw_cnt;
-    uint32_t any_overflow;
-    uint32_t min_filled;
-    uint32_t sticky_overflow;  // like any_overflow but only cleared at the start of a search
-};
 
 // --------------------------------------------------------------- host side
 struct Workspace {
@@ -171,6 +181,11 @@ struct Workspace {
     float *d_thr_f = nullptr;
     uint32_t *d_pend_rows = nullptr;  // floating-point filter paths: rows awaiting exact re-scoring, [nq_cap][pend_cap]
     uint32_t *d_pend_cnt = nullptr;
+    // int8-image path: pairs inside the filter's error band, parked for the whole search with the filter's dot
+    // product and re-checked against the final thresholds (rescore_deferred_kernel)
+    uint32_t *d_defer_rows = nullptr;
+    int *d_defer_dots = nullptr;
+    uint32_t *d_defer_cnt = nullptr;
     __half *d_q16 = nullptr;          // fp16-image path: scaled half queries [nq_cap][dim_pad_h]
     int8_t *d_q8 = nullptr;           // int8-image path: per-query quantised codes [nq_cap][dim_pad8]
     float4 *d_q8_meta = nullptr;      // {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2} per query
@@ -214,9 +229,14 @@ struct Options {
                                      // 2 = always two, 3 = three whenever possible (96-row tiles up to D = 896)
     int ts_chunks = 0;               // K-chunks (8 KB boxes) per stage: 0 = auto (3 when they divide the row, else 2)
     int tc_min_queries = 1;          // int8: the TMA/tcgen05 kernel streams at ~95% of HBM peak even for one query
-    int live = 1;                    // one launch over all rows behind the bootstrap chunk, thresholds maintained in-kernel
-    int live_refresh = 64;           // pushes per query between two in-kernel threshold selections
-    int img8_fused = 1;              // int8-image path: exact re-scoring by warps of the scan kernel itself (no pend lists)
+    int live = 1;                    // one launch over all rows behind a short chunked prefix, thresholds maintained in-kernel:
+                                     // 0 never, 1 when the scan is long enough to amortise it (live_min_rows), 2 whenever possible
+    int live_refresh = 0;            // pushes per query between two in-kernel threshold selections (0 = auto: 32)
+    int img8_defer = 1;              // int8-image path: pairs inside the filter's error band wait for the final thresholds
+    int img8_fused = 1;              // int8-image path, exact re-scoring by warps of the scan kernel itself: 0 never
+                                     // (no live launches either), 1 in live launches, 2 in every launch
+    int64_t live_start_rows = 0;     // rows scanned on the chunked schedule before the live launch (0 = auto)
+    int64_t live_min_rows = 4000000; // live = 1: only when the live launch would cover at least this many rows (2 = always)
 };
 
 // Concurrent small searches (the server issues one query per request thread, 16 pool threads:
@@ -273,6 +293,7 @@ struct Index {
     std::atomic<int64_t> n_combined{0};  // searches that shared a scan with another caller
     // counters
     std::atomic<int64_t> n_searches{0}, n_queries{0}, n_launches{0}, n_scan_launches{0}, n_fallback{0};
+    std::atomic<int64_t> n_live_refreshes{0}, n_live_skips{0}, n_rescored{0}, n_deferred{0};
 };
 
 // rows awaiting exact re-scoring (filter kernels of the floating-point paths)
@@ -280,6 +301,8 @@ struct PendDev {
     uint32_t *rows;  // [nq][cap]
     uint32_t *cnt;   // [nq]
     uint32_t cap;
+    int *dots;       // [nq][cap] the filter's integer dot product (int8-image path: deferred pairs are re-checked
+                     // against the final threshold before their rows are gathered); may be NULL elsewhere
 };
 
 // ---- kernels / launchers (each returns a pkv_status) ----
@@ -299,6 +322,7 @@ int launch_rescore(const Index &ix, const ScanArgs &a, const PendDev &pend, Sear
 bool img8_usable(const Index &ix);
 int build_img8(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);
 int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches);
+int launch_rescore_deferred(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s);
 
 // pkv_operator.cu
 int rank_groups(const float *d_dist, int64_t rows, int nq, const int64_t *d_group_of_row, const float *d_weights,
@@ -309,8 +333,8 @@ int launch_gather_rows(const Index &ix, const int64_t *d_rows, int n, void *d_ou
 int launch_reset_status(Workspace &ws, cudaStream_t s);
 int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);
 int launch_reset_state(Workspace &ws, int nq, cudaStream_t s);
-int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, int64_t *d_ids,
-                  float *d_dist, int32_t *d_counts, cudaStream_t s);
+int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, bool clear_deferred,
+                  int64_t *d_ids, float *d_dist, int32_t *d_counts, cudaStream_t s);
 int launch_finalize(const Index &ix, Workspace &ws, int nq, int k, int64_t *d_ids, float *d_dist, int32_t *d_counts,
                     cudaStream_t s);
 int launch_row_mags(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);

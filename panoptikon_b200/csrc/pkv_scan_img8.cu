@@ -39,23 +39,30 @@ constexpr int CHUNK_BYTES = 128;
 constexpr int MAX_STAGES = 26;
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int RS_WARPS = 6;  // exact re-scoring warps (fused mode): consume the survivors of this CTA's epilogue
+constexpr int RS_WARPS = 2;  // exact re-scoring warps (fused mode): consume the survivors of this CTA's epilogue
+constexpr int RS_SLOTS = 2;  // rows in flight per re-scoring warp (shared-memory buffers filled by cp.async.bulk)
+constexpr int RS_CLAIM = 16; // survivors a re-scoring warp takes off the ring per round
 constexpr int RS_WARP0 = 2 + EPI_WARPS;
 constexpr int IMG_THREADS = 64 + EPI_THREADS + RS_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int HOLD_CAP = 64;
 constexpr int HOLD_FLUSH = 32;
 constexpr float BOUND_CLAMP = 1.07e9f;
-constexpr uint32_t RING_CAP = 1024;  // filter survivors in flight between the epilogue and the re-scoring warps
+constexpr uint32_t RING_CAP = 256;   // filter survivors in flight between the epilogue and the re-scoring warps
 constexpr uint32_t RING_MASK = RING_CAP - 1;
 
 struct ImgArgs {
     const float4 *row_meta;  // [rows] {|a|/s_a, |c|, |a - s_a c|/s_a, 1/s_a}
     const int8_t *q8;        // [nq][dim_pad8] query codes
     const float4 *q_meta;    // [nq] {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2}
-    PendDev pend;            // unfused mode: survivors parked for rescore_kernel
+    PendDev pend;            // unfused mode: survivors parked for rescore_kernel (this chunk's)
+    PendDev dlist;           // defer mode: pairs parked for the whole search (rescore_deferred_kernel)
     int dim_pad8;
     int fused;               // survivors are re-scored by this kernel's own warps (no pend lists, no second launch)
+    int defer;               // only the LIKELY candidates (approximate score beats the threshold) are re-scored right
+                             // away (in-kernel when fused, else by rescore_kernel behind the chunk); pairs inside the
+                             // filter's error band (and, fused, whatever the ring cannot take) are parked with their dot
+                             // product and re-checked against the FINAL thresholds at the end of the search
     int rows_f16;            // stored rows are fp16 (f16 index), else f32
 };
 
@@ -69,6 +76,7 @@ struct ImgShared {
     uint32_t ring_tail;  // tickets handed to consumers (re-scoring warps)
     uint32_t epi_done;   // epilogue warps that have pushed their last survivor
     uint32_t hold_cnt[EPI_WARPS];
+    uint64_t rs_bar[RS_WARPS][RS_SLOTS];  // completion of the re-scoring warps' row copies
     alignas(16) float4 qm[QM_CTA];  // per query {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2} (fixed for the launch)
     float thr[QM_CTA];              // per query: filter threshold (live mode: refreshed tile by tile)
     uint32_t hold_row[EPI_WARPS][HOLD_CAP];
@@ -78,6 +86,7 @@ struct ImgShared {
     // (t % RING_CAP == i) when seq[i] == t, readable when seq[i] == t + 1, and handed on with seq[i] = t + RING_CAP
     uint32_t ring_seq[RING_CAP];
     uint32_t ring_row[RING_CAP];
+    int ring_dot[RING_CAP];  // the filter's integer dot product: re-checked against the fresher threshold at dequeue time
     uint16_t ring_col[RING_CAP];
 };
 
@@ -104,7 +113,7 @@ __device__ __forceinline__ void row_figures(const float4 m, float &x1, float &x2
 // re-scorer's own f32 summation), + 1.
 template <int METRIC>
 __device__ __forceinline__ float pair_bound(const float4 qc, float qs, float x1lo, float x1hi, float x2lo, float x2hi,
-                                            float v, float w, float u) {
+                                            float v, float w, float u, float *lead_out = nullptr) {
     float lead, mag;
     if (METRIC == PKV_L2) {
         const float sum = x1lo + qc.y;  // smallest |a|^2/2 + (|q|^2 - thr)/2 over the rows
@@ -115,6 +124,7 @@ __device__ __forceinline__ float pair_bound(const float4 qc, float qs, float x1l
         mag = fabsf(qc.x) * x1hi;
     }
     const float neg = qc.z * v + qc.w * w;
+    if (lead_out) *lead_out = lead;  // acc >= lead: the APPROXIMATE score already beats the threshold
     return lead - neg - (3e-5f * (mag + neg) + qs * x2hi + 4e-6f * qc.w * u + 1.0f);
 }
 
@@ -134,15 +144,36 @@ __device__ __forceinline__ void query_consts(const float4 qm, float thr, float4 
     qc.w = qm.z;
 }
 
-__device__ __forceinline__ void ring_push(ImgShared *sh, uint32_t row, uint32_t col) {
+__device__ __forceinline__ void ring_push(ImgShared *sh, uint32_t row, uint32_t col, int d) {
     const uint32_t t = atomicAdd(&sh->ring_head, 1u);
     const uint32_t i = t & RING_MASK;
     volatile uint32_t *seq = &sh->ring_seq[i];
-    while (*seq != t) __nanosleep(64);  // ring full: wait for the re-scoring warps (they never wait for us)
+    // ring full: wait for the re-scoring warps (they never wait for us); a wait that never ends is a bug: trap
+    for (uint32_t spins = 0; *seq != t; ++spins) {
+        __nanosleep(64);
+        if (spins > (1u << 24)) __trap();
+    }
     sh->ring_row[i] = row;
+    sh->ring_dot[i] = d;
     sh->ring_col[i] = (uint16_t)col;
     __threadfence_block();
     *seq = t + 1u;
+}
+
+// Non-blocking variant: false when the ring is full.
+__device__ __forceinline__ bool ring_try_push(ImgShared *sh, uint32_t row, uint32_t col, int d) {
+    for (;;) {
+        const uint32_t t = *(volatile uint32_t *)&sh->ring_head;
+        const uint32_t i = t & RING_MASK;
+        if (*(volatile uint32_t *)&sh->ring_seq[i] != t) return false;  // the slot's previous entry is still unread
+        if (atomicCAS(&sh->ring_head, t, t + 1u) != t) continue;
+        sh->ring_row[i] = row;
+        sh->ring_dot[i] = d;
+        sh->ring_col[i] = (uint16_t)col;
+        __threadfence_block();
+        *(volatile uint32_t *)&sh->ring_seq[i] = t + 1u;
+        return true;
+    }
 }
 
 // One pre-filter survivor: exact per-pair bound, membership, then hand the row on for exact re-scoring.
@@ -157,21 +188,35 @@ __device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, 
     float4 qc;
     float qs;
     query_consts<METRIC>(sh->qm[col], *(volatile const float *)&sh->thr[col], qc, qs);
-    const float b = pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x);
+    float lead;
+    const float b = pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x, &lead);
     if ((float)d < b) return;  // NaN bound (non-finite row or query): kept
     if (!topk_member(a.topk, q, row)) return;
+    const bool likely = !((float)d < lead);  // the approximate score beats the threshold (or the pair is unfilterable)
     if (im.fused) {
-        ring_push(sh, row, (uint32_t)col);
+        if (!im.defer) {
+            ring_push(sh, row, (uint32_t)col, d);
+            return;
+        }
+        if (likely && ring_try_push(sh, row, (uint32_t)col, d)) return;  // the in-kernel re-scorer, if it has room
+    } else if (!im.defer || likely) {
+        const uint32_t slot = atomicAdd(im.pend.cnt + q, 1u);
+        if (slot < im.pend.cap) im.pend.rows[(size_t)q * im.pend.cap + slot] = row;
         return;
     }
-    const uint32_t slot = atomicAdd(im.pend.cnt + q, 1u);
-    if (slot < im.pend.cap) im.pend.rows[(size_t)q * im.pend.cap + slot] = row;
+    const uint32_t slot = atomicAdd(im.dlist.cnt + q, 1u);
+    if (slot < im.dlist.cap) {
+        im.dlist.rows[(size_t)q * im.dlist.cap + slot] = row;
+        im.dlist.dots[(size_t)q * im.dlist.cap + slot] = d;
+    }
 }
 
 // ---- exact re-scoring inside the scan kernel (fused mode) -----------------------------------------
-// One warp, two (row, query) pairs at a time: twice the loads in flight per warp.  Same element order, same fmaf
-// chains and the same xor tree as rescore_kernel / the CUDA-core scan, so the reported score of a pair does not
-// depend on which kernel computed it.
+// A re-scoring warp owns RS_SLOTS row buffers in shared memory.  It claims up to RS_SLOTS survivors from the CTA's
+// ring, has the TMA engine copy their stored rows (cp.async.bulk, one mbarrier per slot: no registers are tied up by
+// the gathers, RS_WARPS x RS_SLOTS rows are in flight per SM), loads the query from L2 meanwhile, and computes the
+// exact score with the element order, the fmaf chains and the xor tree of rescore_kernel / the CUDA-core scan, so the
+// reported score of a pair does not depend on which kernel computed it.
 template <int METRIC>
 __device__ __forceinline__ void acc_f4(const float4 av, const float4 qv, float &acc, float &nrm) {
     if (METRIC == PKV_L2) {
@@ -226,66 +271,81 @@ __device__ __forceinline__ float exact_distance(float acc, float nrm, float qmag
     return -acc;
 }
 
+// 1-D bulk copy global -> shared, completion (bytes) signalled on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc::smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+
+// Sums of (row in the shared-memory slot, query q), reduced over the warp (every lane ends up with the totals).
 template <int METRIC>
-__device__ __noinline__ void rescore_two(const ScanArgs &a, const ImgArgs &im, int qA, uint32_t rowA, bool haveB, int qB,
-                                         uint32_t rowB, int lane) {
+__device__ __forceinline__ void score_slot(const ScanArgs &a, const ImgArgs &im, const uint8_t *slot, int q, uint64_t *bar,
+                                           uint32_t phase, int lane, float &acc, float &nrm) {
     const int nvec = a.dim_pad >> 2;  // float4 per padded f32 query
-    const uint8_t *rbA = (const uint8_t *)a.data + (size_t)rowA * (size_t)a.pitch_bytes;
-    const uint8_t *rbB = (const uint8_t *)a.data + (size_t)rowB * (size_t)a.pitch_bytes;
-    const float4 *qpA = (const float4 *)a.queries + (size_t)qA * nvec;
-    const float4 *qpB = (const float4 *)a.queries + (size_t)qB * nvec;
-    float accA = 0.f, nrmA = 0.f, accB = 0.f, nrmB = 0.f;
+    const float4 *qp = (const float4 *)a.queries + (size_t)q * nvec;
+    // the query (<= 4 KB, L2 resident) is fetched while the row copy is in flight.  f32 rows: step `it` of a lane uses
+    // query float4 lane + 32 it; f16 rows (8 halfs per lane per step, scan_f16_simt_kernel's order): float4 2j, 2j + 1
+    // of step j = lane + 32 it
+    float4 qv[8];
     if (!im.rows_f16) {
-        const float4 *rpA = (const float4 *)rbA, *rpB = (const float4 *)rbB;
-#pragma unroll 2
-        for (int j = lane; j < nvec; j += 32) {
-            const float4 avA = ldg_stream_f4(rpA + j), avB = ldg_stream_f4(rpB + j);
-            const float4 qvA = __ldg(qpA + j), qvB = __ldg(qpB + j);
-            acc_f4<METRIC>(avA, qvA, accA, nrmA);
-            acc_f4<METRIC>(avB, qvB, accB, nrmB);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int j = lane + 32 * it;
+            qv[it] = j < nvec ? __ldg(qp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
-        const uint4 *rpA = (const uint4 *)rbA, *rpB = (const uint4 *)rbB;
-        const int nvec8 = a.dim_pad >> 3;  // 8 halfs per lane per step, as scan_f16_simt_kernel
-#pragma unroll 2
-        for (int j = lane; j < nvec8; j += 32) {
-            const uint4 rA = __ldg(rpA + j), rB = __ldg(rpB + j);
-            acc_h8<METRIC>(rA, __ldg(qpA + 2 * j), __ldg(qpA + 2 * j + 1), accA, nrmA);
-            acc_h8<METRIC>(rB, __ldg(qpB + 2 * j), __ldg(qpB + 2 * j + 1), accB, nrmB);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int j = lane + 32 * it;
+            const bool ok = 2 * j + 1 < nvec;
+            qv[2 * it] = ok ? __ldg(qp + 2 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            qv[2 * it + 1] = ok ? __ldg(qp + 2 * j + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc::mbar_wait(bar, phase);
+    acc = 0.f;
+    nrm = 0.f;
+    if (!im.rows_f16) {
+        const float4 *rp = (const float4 *)slot;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int j = lane + 32 * it;
+            if (j < nvec) acc_f4<METRIC>(rp[j], qv[it], acc, nrm);
+        }
+    } else {
+        const uint4 *rp = (const uint4 *)slot;
+        const int nvec8 = a.dim_pad >> 3;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int j = lane + 32 * it;
+            if (j < nvec8) acc_h8<METRIC>(rp[j], qv[2 * it], qv[2 * it + 1], acc, nrm);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        accA += __shfl_xor_sync(0xffffffffu, accA, o);
-        accB += __shfl_xor_sync(0xffffffffu, accB, o);
-        if (METRIC == PKV_COSINE) {
-            nrmA += __shfl_xor_sync(0xffffffffu, nrmA, o);
-            nrmB += __shfl_xor_sync(0xffffffffu, nrmB, o);
-        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (METRIC == PKV_COSINE) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     }
-    // lane 0 pushes pair A, lane 1 pair B
-    int trig_q = -1;
-    if (lane == 0 || (lane == 1 && haveB)) {
-        const int q = lane == 0 ? qA : qB;
-        const uint32_t row = lane == 0 ? rowA : rowB;
-        const float d = exact_distance<METRIC>(lane == 0 ? accA : accB, lane == 0 ? nrmA : nrmB, __ldg(a.q_mag_f + q));
-        if (a.topk.live) {
-            if (topk_push_live(a.topk, q, row, d)) trig_q = q;
-        } else {
-            topk_push(a.topk, q, row, d);
-        }
-    }
-    __syncwarp();
-    if (a.topk.live) live_refresh_pending<16>(a.topk, trig_q, lane);
 }
 
-// lane 0: is ring entry `t` published?  On success the payload is read and the slot handed back to the producers.
-__device__ __forceinline__ bool ring_take(ImgShared *sh, uint32_t t, uint32_t &row, uint32_t &col) {
+// Claims the next ring entry if one has been handed out to a producer (it is then published within a few
+// instructions), reads it and returns the slot to the producers.  false: nothing to take right now.
+__device__ __forceinline__ bool ring_claim(ImgShared *sh, uint32_t &row, uint32_t &col, int &d) {
+    uint32_t t;
+    for (;;) {
+        t = *(volatile uint32_t *)&sh->ring_tail;
+        if ((int32_t)(*(volatile uint32_t *)&sh->ring_head - t) <= 0) return false;
+        if (atomicCAS(&sh->ring_tail, t, t + 1u) == t) break;
+    }
     const uint32_t i = t & RING_MASK;
     volatile uint32_t *seq = &sh->ring_seq[i];
-    if (*seq != t + 1u) return false;
+    for (uint32_t spins = 0; *seq != t + 1u; ++spins)  // the producer holding this ticket is a few instructions away
+        if (spins > (1u << 28)) __trap();
     __threadfence_block();
     row = *(volatile uint32_t *)&sh->ring_row[i];
+    d = *(volatile int *)&sh->ring_dot[i];
     col = *(volatile uint16_t *)&sh->ring_col[i];
     __threadfence_block();
     *seq = t + RING_CAP;
@@ -293,56 +353,140 @@ __device__ __forceinline__ bool ring_take(ImgShared *sh, uint32_t t, uint32_t &r
 }
 
 // Re-scoring warp: consumes ring entries until the CTA's epilogue warps are done and the ring is drained.
+// Per round: up to RS_CLAIM entries are claimed (lane e holds entry e); in live mode each is checked once more
+// against the threshold of NOW (entries wait in the ring while every CTA keeps tightening the thresholds - during the
+// first tiles of a launch most of them have become hopeless by the time they are dequeued); the rest are gathered
+// RS_SLOTS at a time.
 template <int METRIC>
-__device__ __forceinline__ void rescore_loop(const ScanArgs &a, const ImgArgs &im, ImgShared *sh, int qbase,
-                                             uint32_t epi_expected, int lane) {
-    bool have_pending = false;
-    uint32_t pending_t = 0;
+__device__ __forceinline__ void rescore_loop(const ScanArgs &a, const ImgArgs &im, ImgShared *sh, uint8_t *slots,
+                                             uint64_t *bars, int qbase, uint32_t epi_expected, int rw, int lane) {
+    const uint32_t row_bytes = (uint32_t)a.pitch_bytes;
+    uint32_t phase = 0;  // bit s: parity the next completion of slot s will have
+    uint32_t done = 0;
+    constexpr int TPL = QM_CTA / (RS_WARPS * 32);  // thresholds this lane publishes per round
     for (;;) {
-        // ---- entry A: own a ticket, wait until it is published (or can never be) ----
-        uint32_t rowA = 0, colA = 0, rowB = 0, colB = 0;
-        int state = 0;  // 0: drained, 1: A only, 2: A and B
+        // ---- live mode: the CTA's thresholds are published in shared memory by THESE warps (the epilogue threads read
+        // them there once per tile: a global load in their per-tile path stalls the accumulator hand-off).  The loads
+        // are issued now and stored behind this round's work.
+        float tv[TPL];
+        if (a.topk.live) {
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int q = qbase + rw * 32 + lane + i * RS_WARPS * 32;
+                tv[i] = q < a.nq ? ld_live_f32(a.topk.thr_f + q) : 0.f;
+            }
+        }
+        // ---- claim: lane 0 waits a little for the first entry (or the end of the CTA's scan), lanes 1.. take what is there
+        uint32_t row = 0, col = 0;
+        int d = 0;
+        bool have = false;
+        int state = 0;  // 0: nothing yet, 1: an entry, 2: the scan is over and the ring is empty
         if (lane == 0) {
-            const uint32_t tA = have_pending ? pending_t : atomicAdd(&sh->ring_tail, 1u);
-            have_pending = false;
-            for (;;) {
-                if (ring_take(sh, tA, rowA, colA)) {
+            for (int spin = 0; spin < 8; ++spin) {
+                if (ring_claim(sh, row, col, d)) {
                     state = 1;
                     break;
                 }
                 if (*(volatile uint32_t *)&sh->epi_done >= epi_expected) {
-                    // every producer has published its last entry: the head is final
                     __threadfence_block();
-                    if ((int32_t)(tA - *(volatile uint32_t *)&sh->ring_head) >= 0) break;
-                    continue;  // the entry exists: take it on the next poll
+                    state = ring_claim(sh, row, col, d) ? 1 : 2;  // the head is final now
+                    break;
                 }
                 __nanosleep(128);
             }
-            // ---- entry B, only if one is already there (never wait for a partner while holding A) ----
-            if (state == 1 && (int32_t)(*(volatile uint32_t *)&sh->ring_head - *(volatile uint32_t *)&sh->ring_tail) > 0) {
-                const uint32_t tB = atomicAdd(&sh->ring_tail, 1u);
-                bool got = false;
-                for (int spin = 0; spin < 16 && !got; ++spin) got = ring_take(sh, tB, rowB, colB);
-                if (got) {
-                    state = 2;
-                } else {
-                    have_pending = true;  // still ours: becomes entry A of the next round
-                    pending_t = tB;
-                }
-            }
+            have = state == 1;
         }
         state = __shfl_sync(0xffffffffu, state, 0);
-        if (state == 0) break;
-        rowA = __shfl_sync(0xffffffffu, rowA, 0);
-        colA = __shfl_sync(0xffffffffu, colA, 0);
-        rowB = __shfl_sync(0xffffffffu, rowB, 0);
-        colB = __shfl_sync(0xffffffffu, colB, 0);
-        if (state == 1) {
-            rowB = rowA;
-            colB = colA;
+        if (a.topk.live) {
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int c = rw * 32 + lane + i * RS_WARPS * 32;
+                if (qbase + c < a.nq) *(volatile float *)&sh->thr[c] = tv[i];
+            }
         }
-        rescore_two<METRIC>(a, im, qbase + (int)colA, rowA, state == 2, qbase + (int)colB, rowB, lane);
+        if (state == 2) break;
+        if (state == 0) continue;
+        if (lane > 0 && lane < RS_CLAIM) have = ring_claim(sh, row, col, d);
+        // ---- late re-check against the live threshold
+        if (have && a.topk.live) {
+            const int q = qbase + (int)col;
+            float4 qc;
+            float qs;
+            query_consts<METRIC>(sh->qm[col], ld_live_f32(a.topk.thr_f + q), qc, qs);
+            const float4 m = __ldg(im.row_meta + row);
+            float x1, x2;
+            row_figures<METRIC>(m, x1, x2);
+            if ((float)d < pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x)) have = false;
+        }
+        // the CTA's scan is over: what is still queued joins the parked pairs (the launch behind this one gathers with
+        // every warp of the GPU and the final thresholds) instead of keeping 146 idle SMs waiting for two warps
+        // (one lane reads the flag: the decision must be the same for the whole warp)
+        const uint32_t scan_over =
+            __shfl_sync(0xffffffffu, (uint32_t)(*(volatile uint32_t *)&sh->epi_done >= epi_expected), 0);
+        if (im.defer && scan_over) {
+            if (have) {
+                const int q = qbase + (int)col;
+                const uint32_t slot = atomicAdd(im.dlist.cnt + q, 1u);
+                if (slot < im.dlist.cap) {
+                    im.dlist.rows[(size_t)q * im.dlist.cap + slot] = row;
+                    im.dlist.dots[(size_t)q * im.dlist.cap + slot] = d;
+                }
+            }
+            continue;
+        }
+        const unsigned todo = __ballot_sync(0xffffffffu, have);
+        if (!todo) continue;
+        // ---- gather + score: the warp's RS_SLOTS row buffers form a pipeline - while entry i is scored, the TMA
+        // engine is already copying entries i + 1 .. i + RS_SLOTS - 1; entry i's sums stay in the lane that holds it
+        const int n = __popc(todo);
+        unsigned issue_rem = todo, proc_rem = todo;
+        float my_acc = 0.f, my_nrm = 0.f;
+        auto issue_next = [&](int slot) {
+            const int src = __ffs(issue_rem) - 1;
+            issue_rem &= issue_rem - 1u;
+            const uint32_t r = __shfl_sync(0xffffffffu, row, src);
+            if (lane == 0) {
+                // the warp has finished reading this slot (generic proxy) before the TMA engine rewrites it
+                tc::fence_proxy_async();
+                tc::mbar_expect_tx(&bars[slot], row_bytes);
+                bulk_g2s(slots + (size_t)slot * row_bytes, (const uint8_t *)a.data + (size_t)r * (size_t)a.pitch_bytes,
+                         row_bytes, &bars[slot]);
+            }
+        };
+#pragma unroll
+        for (int s0 = 0; s0 < RS_SLOTS; ++s0)
+            if (s0 < n) issue_next(s0);
+        for (int i = 0; i < n; ++i) {
+            const int slot = i % RS_SLOTS;
+            const int src = __ffs(proc_rem) - 1;
+            proc_rem &= proc_rem - 1u;
+            const int q = qbase + (int)__shfl_sync(0xffffffffu, col, src);
+            float acc, nrm;
+            score_slot<METRIC>(a, im, slots + (size_t)slot * row_bytes, q, &bars[slot], (phase >> slot) & 1u, lane, acc, nrm);
+            phase ^= 1u << slot;
+            if (lane == src) {
+                my_acc = acc;
+                my_nrm = nrm;
+            }
+            __syncwarp();
+            if (issue_rem) issue_next(slot);
+        }
+        done += (uint32_t)n;
+        // ---- every lane finishes its own pair: exact key, push, refresh request
+        int trig_q = -1;
+        if (have) {
+            const int q = qbase + (int)col;
+            const float dist = exact_distance<METRIC>(my_acc, my_nrm, __ldg(a.q_mag_f + q));
+            if (a.topk.live) {
+                if (topk_push_live(a.topk, q, row, dist)) trig_q = q;
+            } else {
+                topk_push(a.topk, q, row, dist);
+            }
+        }
+        __syncwarp();
+        if (a.topk.live) live_refresh_pending<16>(a.topk, trig_q, lane);
     }
+    if (lane == 0 && done) atomicAdd(&a.topk.status->rescored, done);
 }
 
 template <int METRIC>
@@ -385,7 +529,7 @@ __device__ __forceinline__ float warp_max_nn(float v) {
 template <int METRIC, int CPS, bool PAIR, int TN, int NBUF>
 __global__ void __launch_bounds__(IMG_THREADS, 1)
 scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a, const ImgArgs im, const int q0,
-                 const int groups, const int kchunks, const int stages) {
+                 const int groups, const int kchunks, const int stages, const int rs_bytes) {
     constexpr int TILE_N = TN;
     constexpr int EPI_USED = (TN / 32) * 4;            // epilogue warps with work: 32 accumulator columns each
     const uint32_t acc_col0 = (uint32_t)(im.dim_pad8 / 4 + 31) / 32 * 32;  // accumulators behind the query columns
@@ -397,7 +541,8 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
     uint8_t *smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t *s_b = smem;  // [stages][CPS chunks][ROWS_CTA rows][128 B]
-    ImgShared *sh = reinterpret_cast<ImgShared *>(s_b + (size_t)stages * STAGE_BYTES);
+    uint8_t *rs_slots = s_b + (size_t)stages * STAGE_BYTES;  // [RS_WARPS][RS_SLOTS][row pitch] (fused mode)
+    ImgShared *sh = reinterpret_cast<ImgShared *>(rs_slots + rs_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
@@ -418,6 +563,8 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             tc::mbar_init(&sh->tmem_empty[b], NCTA * EPI_USED);
         }
         for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
+        for (int w = 0; w < RS_WARPS; ++w)
+            for (int b = 0; b < RS_SLOTS; ++b) tc::mbar_init(&sh->rs_bar[w][b], 1);
         sh->ring_head = 0;
         sh->ring_tail = 0;
         sh->epi_done = 0;
@@ -571,20 +718,15 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         bool row_ok = seq < ntiles && nrow < a.row_end;
         float4 m = row_ok ? __ldg(im.row_meta + nrow) : make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t empty0 = PAIR ? tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0) : tc::smem_u32(&sh->tmem_empty[0]);
-        // live mode: the query's threshold is re-read from global memory once per tile (the re-scoring warps of every
-        // CTA tighten it while the scan runs); the value for the next tile is fetched behind this tile's work
+        // live mode: the query's threshold is re-read once per tile from shared memory, where this CTA's re-scoring
+        // warps keep publishing what every CTA's re-scoring warps tighten in global memory while the scan runs
         const bool live = a.topk.live != 0 && real_q;
-        float thr_next = thr0;
         float4 qc;
         float qs;
         query_consts<METRIC>(qm, thr0, qc, qs);
         for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
-            if (live) {
-                query_consts<METRIC>(qm, thr_next, qc, qs);
-                if ((ew >> 2) == 0) *(volatile float *)&sh->thr[qcol] = thr_next;  // per-pair bound of consider_img
-                thr_next = ld_live_f32(a.topk.thr_f + qbase + qcol);
-            }
+            if (live) query_consts<METRIC>(qm, *(volatile const float *)&sh->thr[qcol], qc, qs);
             // loosest figures over the warp's 32 rows (rows past the end must not loosen them)
             float x1, x2;
             row_figures<METRIC>(m, x1, x2);
@@ -634,7 +776,11 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         }
     } else if (warp >= RS_WARP0) {
         // ===================== exact re-scoring of this CTA's filter survivors (fused mode) =====================
-        if (im.fused) rescore_loop<METRIC>(a, im, sh, qbase, seq < nseq ? (uint32_t)EPI_USED : 0u, lane);
+        if (im.fused) {
+            const int rw = warp - RS_WARP0;
+            rescore_loop<METRIC>(a, im, sh, rs_slots + (size_t)rw * RS_SLOTS * (size_t)a.pitch_bytes, sh->rs_bar[rw], qbase,
+                                 seq < nseq ? (uint32_t)EPI_USED : 0u, rw, lane);
+        }
     }
 
     tc::fence_before_sync();
@@ -644,6 +790,70 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         if (PAIR) tc::tmem_dealloc_cta2(tmem_base, TMEM_COLS);
         else tc::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Behind a live launch: the pairs it parked (inside the filter's error band, or more than the in-kernel re-scorer
+// could take) are checked once more - against the threshold the WHOLE scan arrived at - and only what still cannot be
+// excluded is gathered and scored exactly.  One CTA per (query, slice); the check runs lane-parallel, the gathers one
+// warp per pair with the summation order of rescore_kernel.
+template <int METRIC, bool ROWS_F16>
+__global__ void __launch_bounds__(256) rescore_deferred_kernel(const ScanArgs a, const ImgArgs im, SearchStatus *status) {
+    extern __shared__ float4 s_q[];  // one query, dim_pad/4 float4 (f32, widened for an f16 index)
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int nvec = a.dim_pad >> 2;
+    const uint32_t raw = im.dlist.cnt[q];
+    const uint32_t n = raw < im.dlist.cap ? raw : im.dlist.cap;
+    if (blockIdx.y == 0 && threadIdx.x == 0 && raw > im.dlist.cap) atomicOr(&status->defer_overflow, 1u);
+    if (n == 0) return;
+    const float4 *gq = (const float4 *)a.queries + (size_t)q * nvec;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) s_q[i] = gq[i];
+    __syncthreads();
+    float4 qc;
+    float qs;
+    query_consts<METRIC>(__ldg(im.q_meta + q), a.topk.thr_f[q], qc, qs);
+    const float qmag = __ldg(a.q_mag_f + q);
+    const uint32_t nwarps = gridDim.y * (blockDim.x >> 5);
+    const uint32_t wid = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t gathered = 0;
+    for (uint32_t base = wid * 32u; base < n; base += nwarps * 32u) {
+        const uint32_t e = base + lane;
+        uint32_t row = 0;
+        bool keep = false;
+        if (e < n) {
+            row = im.dlist.rows[(size_t)q * im.dlist.cap + e];
+            const int d = im.dlist.dots[(size_t)q * im.dlist.cap + e];
+            const float4 m = __ldg(im.row_meta + row);
+            float x1, x2;
+            row_figures<METRIC>(m, x1, x2);
+            keep = !((float)d < pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x));
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, keep);
+        gathered += (uint32_t)__popc(todo);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t r = __shfl_sync(0xffffffffu, row, src);
+            const uint8_t *rb = (const uint8_t *)a.data + (size_t)r * (size_t)a.pitch_bytes;
+            float acc = 0.f, nrm = 0.f;
+            if (!ROWS_F16) {
+                const float4 *rp = (const float4 *)rb;
+                for (int j = lane; j < nvec; j += 32) acc_f4<METRIC>(__ldg(rp + j), s_q[j], acc, nrm);
+            } else {
+                const uint4 *rp = (const uint4 *)rb;
+                const int nvec8 = a.dim_pad >> 3;
+                for (int j = lane; j < nvec8; j += 32) acc_h8<METRIC>(__ldg(rp + j), s_q[2 * j], s_q[2 * j + 1], acc, nrm);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (METRIC == PKV_COSINE) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+            }
+            if (lane == 0) topk_push(a.topk, q, r, exact_distance<METRIC>(acc, nrm, qmag));
+        }
+    }
+    if (lane == 0 && gathered) atomicAdd(&status->deferred, gathered);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -809,10 +1019,12 @@ int launch_img8(const Index &ix, const ScanArgs &a, const ImgArgs &im, int q0, i
     CUtensorMap mrows;
     PKV_TRY(make_tmap_bytes(&mrows, ix.d_img8, (uint64_t)ix.dim_pad8, (uint64_t)ix.sealed_rows, (uint64_t)ix.dim_pad8, ROWS_CTA));
     const size_t ctrl = sizeof(ImgShared);
-    int stages = (int)((227 * 1024 - 1024 - ctrl) / STAGE_BYTES);
+    const size_t rs_bytes = im.fused ? (size_t)RS_WARPS * RS_SLOTS * (size_t)ix.pitch : 0;  // the re-scoring warps' row buffers
+    int stages = (int)((227 * 1024 - 1024 - ctrl - rs_bytes) / STAGE_BYTES);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (ix.opt.ts_stages > 1 && ix.opt.ts_stages < stages) stages = ix.opt.ts_stages;
-    const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + ctrl;
+    if (stages < 2) return fail(PKV_ERR_UNSUPPORTED, "dim %d leaves no room for the row stages", ix.dim);
+    const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + rs_bytes + ctrl;
     auto kernel = scan_img8_kernel<METRIC, CPS, PAIR, TN, NBUF>;
     PKV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t ntiles = (a.row_end - a.row_begin + TN - 1) / TN;
@@ -832,7 +1044,7 @@ int launch_img8(const Index &ix, const ScanArgs &a, const ImgArgs &im, int q0, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PKV_CUDA(cudaLaunchKernelEx(&cfg, kernel, mrows, a, im, q0, groups, kchunks, stages));
+    PKV_CUDA(cudaLaunchKernelEx(&cfg, kernel, mrows, a, im, q0, groups, kchunks, stages, (int)rs_bytes));
     return PKV_OK;
 }
 
@@ -920,18 +1132,55 @@ int build_img8(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) {
     return PKV_OK;
 }
 
-int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
-    if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
+static ImgArgs img_args(const Index &ix, const ScanArgs &a, Workspace &ws) {
     ImgArgs im;
     im.row_meta = ix.d_img8_meta;
     im.q8 = ws.d_q8;
     im.q_meta = ws.d_q8_meta;
-    im.pend = PendDev{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap};
+    im.pend = PendDev{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap, nullptr};
+    im.dlist = PendDev{ws.d_defer_rows, ws.d_defer_cnt, (uint32_t)ws.pend_cap, ws.d_defer_dots};
     im.dim_pad8 = ix.dim_pad8;
     // live launches always re-score in-kernel: the thresholds can only move while the scan runs if the exact
-    // scores are produced while it runs
-    im.fused = (ix.opt.img8_fused || a.topk.live) ? 1 : 0;
+    // scores are produced while it runs.  The chunks before it keep the separate re-score kernel (every SM gathers
+    // with all its warps: the early chunks pass many more rows than the scan's own few warps can take)
+    im.fused = (ix.opt.img8_fused >= 2 || a.topk.live) ? 1 : 0;
+    im.defer = a.topk.defer;
     im.rows_f16 = ix.dtype == PKV_F16 ? 1 : 0;
+    return im;
+}
+
+// The pairs parked by the chunks of a search, against the thresholds the scan ended with (before the last select).
+int launch_rescore_deferred(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s) {
+    if (a.nq <= 0) return PKV_OK;
+    const ImgArgs im = img_args(ix, a, ws);
+    const size_t smem = (size_t)a.dim_pad * 4;
+    int ry = (4 * ix.sm_count + a.nq - 1) / a.nq;  // ~4 CTAs per SM in total
+    if (ry < 1) ry = 1;
+    if (ry > 64) ry = 64;
+    const dim3 grid((unsigned)a.nq, (unsigned)ry);
+#define PKV_DEFERRED(M)                                                                                  \
+    do {                                                                                                 \
+        if (ix.dtype == PKV_F16) {                                                                       \
+            auto rk = rescore_deferred_kernel<M, true>;                                                  \
+            PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            rk<<<grid, 256, smem, s>>>(a, im, ws.d_status);                                              \
+        } else {                                                                                         \
+            auto rk = rescore_deferred_kernel<M, false>;                                                 \
+            PKV_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            rk<<<grid, 256, smem, s>>>(a, im, ws.d_status);                                              \
+        }                                                                                                \
+    } while (0)
+    if (a.metric == PKV_COSINE) PKV_DEFERRED(PKV_COSINE);
+    else if (a.metric == PKV_L2) PKV_DEFERRED(PKV_L2);
+    else PKV_DEFERRED(PKV_DOT);
+#undef PKV_DEFERRED
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
+int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
+    if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
+    ImgArgs im = img_args(ix, a, ws);
     // pend counters are zeroed by reset_state_kernel / select_kernel; the query codes are made once per search
     if (!ws.q8_ready) {
         img8_prep_queries_kernel<<<(a.nq + 7) / 8, 256, 0, s>>>((const float *)a.queries, a.nq, ix.dim, ix.dim_pad,

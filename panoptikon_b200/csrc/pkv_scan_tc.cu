@@ -32,7 +32,9 @@ constexpr int QCHUNK_BYTES = TILE_N * CHUNK_BYTES;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_WARPS = 16;       // four warps per TMEM lane quarter, 32 columns each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TC_THREADS = 64 + EPI_THREADS;
+constexpr int SV_WARPS = 2;         // service warps (live mode): thresholds into shared memory, in-kernel threshold selections
+constexpr int SV_WARP0 = 2 + EPI_WARPS;
+constexpr int TC_THREADS = 64 + EPI_THREADS + SV_WARPS * 32;
 constexpr int TMEM_COLS = 2 * TILE_N;  // double-buffered accumulator
 constexpr int COLS_PER_WARP = TILE_N / 4;
 constexpr int HOLD_CAP = 64;        // staged pre-filter survivors per epilogue warp
@@ -47,6 +49,8 @@ struct TcShared {  // control block behind the data stages
     uint32_t tmem_base;
     uint32_t pad;
     uint32_t hold_cnt[EPI_WARPS];
+    uint32_t epi_done;                 // epilogue warps that have finished their tiles
+    uint32_t refresh_req[TILE_N];      // live mode: a push of this query hit its refresh trigger
     alignas(16) float thr[TILE_N];  // per query: filter threshold thr_f (metric specific)
     float tq[TILE_N];        // per query: finite, clamped figure the integer bound is derived from
     int q_mag[TILE_N];       // per query: integer squared norm
@@ -57,21 +61,23 @@ struct TcShared {  // control block behind the data stages
 };
 
 // Exact filter, exact key, candidate push for one pre-filter survivor.
-// Returns the query whose threshold this push asks the warp to re-select (live mode), else -1.
+// Live mode: a push that hits the query's refresh trigger leaves a request for the service warps.
 template <int METRIC>
-__device__ __noinline__ int consider(const ScanArgs &a, int q0, int col, int d, uint32_t row, const TcShared *sh) {
+__device__ __noinline__ void consider(const ScanArgs &a, int q0, int col, int d, uint32_t row, TcShared *sh) {
     const int q = q0 + col;
-    if (q >= a.nq || row >= a.row_end) return -1;
+    if (q >= a.nq || row >= a.row_end) return;
     const int am = __ldg(a.row_mag_i + row);
     const int bm = sh->q_mag[col];
-    if (!exact_filter<METRIC>(d, am, bm, *(volatile const float *)&sh->thr[col])) return -1;
-    if (!topk_member(a.topk, q, row)) return -1;
+    if (!exact_filter<METRIC>(d, am, bm, *(volatile const float *)&sh->thr[col])) return;
+    if (!topk_member(a.topk, q, row)) return;
     const int8_t *rowp = (const int8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
     const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
     const float key = i8_key(METRIC, d, am, bm, a.dim, rowp, qp);
-    if (a.topk.live) return topk_push_live(a.topk, q, row, key) ? q : -1;
-    topk_push(a.topk, q, row, key);
-    return -1;
+    if (a.topk.live) {
+        if (topk_push_live(a.topk, q, row, key)) *(volatile uint32_t *)&sh->refresh_req[col] = 1u;
+    } else {
+        topk_push(a.topk, q, row, key);
+    }
 }
 
 // A lane found a pre-filter survivor: park it in its warp's shared-memory list (cheap) so that the
@@ -95,15 +101,11 @@ __device__ __forceinline__ void flush_held(const ScanArgs &a, int q0, TcShared *
     const uint32_t cnt = sh->hold_cnt[ew];
     if (cnt < min_cnt) return;
     const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
-    int trig_q = -1;
-    for (uint32_t e = lane; e < n; e += 32) {
-        const int t = consider<METRIC>(a, q0, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
-        if (t >= 0) trig_q = t;
-    }
+    for (uint32_t e = lane; e < n; e += 32)
+        consider<METRIC>(a, q0, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
     __syncwarp();
     if (lane == 0) sh->hold_cnt[ew] = 0;
     __syncwarp();
-    if (a.topk.live) live_refresh_pending<16>(a.topk, trig_q, lane);
 }
 
 template <int METRIC>
@@ -132,6 +134,7 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             tc::mbar_init(&sh->tmem_empty[b], EPI_WARPS);
         }
         for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
+        sh->epi_done = 0;
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_rows);
         tc::prefetch_tmap(&tmap_q);
@@ -143,6 +146,7 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
     if (warp >= 2) {
         const int col = threadIdx.x - 64;
         if (col < TILE_N) {
+            sh->refresh_req[col] = 0;
             const int q = q0 + col;
             const float thr = q < a.nq ? __ldg(a.topk.thr_f + q) : -__int_as_float(0x7f800000);
             const int bm = q < a.nq ? __ldg(a.q_mag_i + q) : 0;
@@ -211,6 +215,28 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
                 __syncwarp();
             }
         }
+    } else if (warp >= SV_WARP0) {
+        // ===================== service warps (live mode) =====================
+        if (a.topk.live) {
+            const int sw = warp - SV_WARP0;
+            for (;;) {
+                // one lane reads the flag: the whole warp must take the same exit
+            const bool last = __shfl_sync(0xffffffffu, (uint32_t)(*(volatile uint32_t *)&sh->epi_done >= (uint32_t)EPI_WARPS), 0) != 0;
+                for (int c = sw * 32 + lane; c < TILE_N; c += SV_WARPS * 32) {
+                    const int q = q0 + c;
+                    int trig_q = -1;
+                    if (q < a.nq) {
+                        const float thr = ld_live_f32(a.topk.thr_f + q);
+                        *(volatile float *)&sh->thr[c] = thr;
+                        *(volatile float *)&sh->tq[c] = prefilter_query_figure<METRIC>(thr, sh->q_mag[c]);
+                        if (*(volatile uint32_t *)&sh->refresh_req[c] && atomicExch(&sh->refresh_req[c], 0u)) trig_q = q;
+                    }
+                    live_refresh_pending<16>(a.topk, trig_q, lane);
+                }
+                if (last) break;
+                __nanosleep(256);
+            }
+        }
     } else {
         // ===================== epilogue =====================
         const int ew = warp - 2;           // 0..7
@@ -219,18 +245,9 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
         uint32_t t = 0;
         uint32_t row = a.row_begin + blockIdx.x * TILE_M + quarter * 32 + lane;
         int am = (blockIdx.x < ntiles && row < a.row_end) ? __ldg(a.row_mag_i + row) : -1;
-        // live mode: warps 0..3 of the epilogue own one query each and re-read its threshold from global memory once
-        // per tile (other CTAs tighten it while the scan runs); a stale value in shared memory is only looser
-        const int lcol = ew * 32 + lane;
-        const bool live = a.topk.live != 0 && ew < 4 && (q0 + lcol) < a.nq;
-        float thr_next = live ? ld_live_f32(a.topk.thr_f + q0 + lcol) : 0.f;
+        // live mode: the service warps keep sh->thr / sh->tq fresh (a stale value is only looser)
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
             const uint32_t buf = t & 1, bph = (t >> 1) & 1;
-            if (live) {
-                *(volatile float *)&sh->thr[lcol] = thr_next;
-                *(volatile float *)&sh->tq[lcol] = prefilter_query_figure<METRIC>(thr_next, sh->q_mag[lcol]);
-                thr_next = ld_live_f32(a.topk.thr_f + q0 + lcol);
-            }
             const uint32_t cur_row = row;
             const bool row_ok = am >= 0;
             // rows past the end must not loosen (min) the warp's bound
@@ -275,6 +292,8 @@ scan_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_co
             flush_held<METRIC>(a, q0, sh, ew, lane, HOLD_FLUSH);
         }
         flush_held<METRIC>(a, q0, sh, ew, lane, 1);
+        __syncwarp();
+        if (lane == 0) atomicAdd(&sh->epi_done, 1u);
     }
 
     tc::fence_before_sync();

@@ -741,7 +741,7 @@ int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) 
 int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
     if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
     if (image_choice(ix, a.nq) == 2) return launch_scan_img8(ix, a, ws, s, launches);
-    PendDev pend{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap};
+    PendDev pend{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap, nullptr};
     PKV_CUDA(cudaMemsetAsync(ws.d_pend_cnt, 0, sizeof(uint32_t) * a.nq, s));
     FloatScan fsn;
     fsn.eps = float_eps(ix, a.nq);

@@ -36,7 +36,10 @@ constexpr int CHUNK_BYTES = 128;
 constexpr int MAX_STAGES = 26;
 constexpr int EPI_WARPS = 16;   // lane quarter = warp & 3, 32 accumulator columns each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TS_THREADS = 64 + EPI_THREADS;
+constexpr int SV_WARPS = 2;     // service warps (live mode): publish the CTA's thresholds in shared memory and run the
+                                // in-kernel threshold selections the epilogue warps ask for
+constexpr int SV_WARP0 = 2 + EPI_WARPS;
+constexpr int TS_THREADS = 64 + EPI_THREADS + SV_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int HOLD_CAP = 64;
 constexpr int HOLD_FLUSH = 32;
@@ -49,6 +52,8 @@ struct TsShared {
     uint32_t tmem_base;
     uint32_t pad;
     uint32_t hold_cnt[EPI_WARPS];
+    uint32_t epi_done;                 // epilogue warps that have finished their tiles
+    uint32_t refresh_req[QM_CTA];      // live mode: a push of this query hit its refresh trigger
     alignas(16) float thr[QM_CTA];
     alignas(16) int q_mag[QM_CTA];
     uint32_t hold_row[EPI_WARPS][HOLD_CAP];
@@ -57,21 +62,23 @@ struct TsShared {
 };
 
 // Exact filter, exact key, candidate push for one pre-filter survivor (col = query within the CTA).
-// Returns the query whose threshold this push asks the warp to re-select (live mode), else -1.
+// Live mode: a push that hits the query's refresh trigger leaves a request for the service warps.
 template <int METRIC>
-__device__ __noinline__ int consider_ts(const ScanArgs &a, int qbase, int col, int d, uint32_t row, const TsShared *sh) {
+__device__ __noinline__ void consider_ts(const ScanArgs &a, int qbase, int col, int d, uint32_t row, TsShared *sh) {
     const int q = qbase + col;
-    if (q >= a.nq || row >= a.row_end) return -1;
+    if (q >= a.nq || row >= a.row_end) return;
     const int am = __ldg(a.row_mag_i + row);
     const int bm = sh->q_mag[col];
-    if (!exact_filter<METRIC>(d, am, bm, *(volatile const float *)&sh->thr[col])) return -1;
-    if (!topk_member(a.topk, q, row)) return -1;
+    if (!exact_filter<METRIC>(d, am, bm, *(volatile const float *)&sh->thr[col])) return;
+    if (!topk_member(a.topk, q, row)) return;
     const int8_t *rowp = (const int8_t *)a.data + (size_t)row * (size_t)a.pitch_bytes;
     const int8_t *qp = (const int8_t *)a.queries + (size_t)q * a.dim_pad;
     const float key = i8_key(METRIC, d, am, bm, a.dim, rowp, qp);
-    if (a.topk.live) return topk_push_live(a.topk, q, row, key) ? q : -1;
-    topk_push(a.topk, q, row, key);
-    return -1;
+    if (a.topk.live) {
+        if (topk_push_live(a.topk, q, row, key)) *(volatile uint32_t *)&sh->refresh_req[col] = 1u;
+    } else {
+        topk_push(a.topk, q, row, key);
+    }
 }
 
 template <int METRIC>
@@ -92,15 +99,11 @@ __device__ __forceinline__ void flush_ts(const ScanArgs &a, int qbase, TsShared 
     const uint32_t cnt = sh->hold_cnt[ew];
     if (cnt < min_cnt) return;
     const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
-    int trig_q = -1;
-    for (uint32_t e = lane; e < n; e += 32) {
-        const int t = consider_ts<METRIC>(a, qbase, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
-        if (t >= 0) trig_q = t;
-    }
+    for (uint32_t e = lane; e < n; e += 32)
+        consider_ts<METRIC>(a, qbase, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
     __syncwarp();
     if (lane == 0) sh->hold_cnt[ew] = 0;
     __syncwarp();
-    if (a.topk.live) live_refresh_pending<16>(a.topk, trig_q, lane);
 }
 
 // TN = corpus rows per tile (MMA N), NBUF = accumulator buffers in TMEM behind the query columns.  The round trip
@@ -142,6 +145,7 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             tc::mbar_init(&sh->tmem_empty[b], 2 * EPI_USED);
         }
         for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
+        sh->epi_done = 0;
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_rows);
     }
@@ -156,7 +160,8 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
 
     // per-thread query figures (epilogue thread = one query)
     float tq = 0.f;
-    if (warp >= 2) {
+    if (threadIdx.x < QM_CTA) sh->refresh_req[threadIdx.x] = 0;
+    if (warp >= 2 && warp < SV_WARP0) {
         const int ew = warp - 2, quarter = warp & 3;
         const int col = quarter * 32 + lane;
         const int q = qbase + col;
@@ -273,11 +278,10 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
         uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
         int am = (seq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
         const uint32_t empty0 = tc::mapa(tc::smem_u32(&sh->tmem_empty[0]), 0);
-        // live mode: this thread's query threshold is re-read from global memory once per tile (other CTAs tighten it
-        // while the scan runs); the value for the next tile is fetched behind this tile's work
+        // live mode: this thread's query threshold is re-read once per tile from shared memory, where the service warps
+        // publish what the whole grid tightens in global memory (a global load here would stall the accumulator hand-off)
         const bool live = a.topk.live != 0 && (qbase + qcol) < a.nq;
         const int bm_q = live ? sh->q_mag[qcol] : 0;
-        float thr_next = live ? ld_live_f32(a.topk.thr_f + qbase + qcol) : 0.f;
         for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
             const bool row_ok = am >= 0;
@@ -285,11 +289,7 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             const int am_max = __reduce_max_sync(0xffffffffu, row_ok ? am : 0);
             nrow = a.row_begin + (tile + nseq) * TILE_N + col0 + lane;
             am = (tile + nseq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
-            if (live) {
-                tq = prefilter_query_figure<METRIC>(thr_next, bm_q);
-                if ((ew >> 2) == 0) *(volatile float *)&sh->thr[qcol] = thr_next;  // exact filter of consider_ts
-                thr_next = ld_live_f32(a.topk.thr_f + qbase + qcol);
-            }
+            if (live) tq = prefilter_query_figure<METRIC>(*(volatile const float *)&sh->thr[qcol], bm_q);
             const int bound = prefilter_bound<METRIC>(tq, sqrtf((float)am_min), sqrtf((float)am_max), (float)am_min);
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();
@@ -314,6 +314,28 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             flush_ts<METRIC>(a, qbase, sh, ew, lane, HOLD_FLUSH);
         }
         flush_ts<METRIC>(a, qbase, sh, ew, lane, 1);
+        __syncwarp();
+        if (lane == 0) atomicAdd(&sh->epi_done, 1u);
+    } else if (warp >= SV_WARP0 && a.topk.live) {
+        // ===================== service warps (live mode) =====================
+        const int sw = warp - SV_WARP0;
+        const uint32_t expected = seq < nseq ? (uint32_t)EPI_USED : 0u;
+        for (;;) {
+            // one lane reads the flag: the whole warp must take the same exit
+            const bool last = __shfl_sync(0xffffffffu, (uint32_t)(*(volatile uint32_t *)&sh->epi_done >= expected), 0) != 0;
+            int trig_q = -1;
+            for (int c = sw * 32 + lane; c < QM_CTA; c += SV_WARPS * 32) {
+                const int q = qbase + c;
+                if (q < a.nq) {
+                    *(volatile float *)&sh->thr[c] = ld_live_f32(a.topk.thr_f + q);
+                    if (*(volatile uint32_t *)&sh->refresh_req[c] && atomicExch(&sh->refresh_req[c], 0u)) trig_q = q;
+                }
+                live_refresh_pending<16>(a.topk, trig_q, lane);
+                trig_q = -1;
+            }
+            if (last) break;
+            __nanosleep(256);
+        }
     }
 
     tc::fence_before_sync();

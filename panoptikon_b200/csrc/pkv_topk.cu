@@ -70,11 +70,12 @@ __global__ void prep_queries_kernel(const void *qraw, int query_dtype, int index
 }
 
 __global__ void reset_state_kernel(uint32_t *cnt, uint64_t *thr_key, float *thr_f, SearchStatus *st, int nq,
-                                   uint32_t *pend_cnt) {
+                                   uint32_t *pend_cnt, uint32_t *defer_cnt) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq) {
         cnt[i] = 0;
         if (pend_cnt) pend_cnt[i] = 0;
+        if (defer_cnt) defer_cnt[i] = 0;
         thr_key[i] = KEY_MAX;
         thr_f[i] = __int_as_float(0x7f800000);
     }
@@ -83,6 +84,11 @@ __global__ void reset_state_kernel(uint32_t *cnt, uint64_t *thr_key, float *thr_
         st->any_overflow = 0;
         st->min_filled = 0xFFFFFFFFu;
         st->sticky_overflow = 0;
+        st->live_refreshes = 0;
+        st->live_skips = 0;
+        st->rescored = 0;
+        st->deferred = 0;
+        st->defer_overflow = 0;
     }
 }
 
@@ -100,7 +106,7 @@ __global__ void reset_status_kernel(SearchStatus *st) {
 //   out_ids != NULL: this is the last select of the search; the result rows are written here too (no finalize launch).
 __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *cnt, uint64_t *thr_key, float *thr_f,
                                                      const float *q_mag_f, SearchStatus *status, uint32_t cap, int k,
-                                                     FilterSpec fs, uint32_t *pend_cnt, int clear_tail,
+                                                     FilterSpec fs, uint32_t *pend_cnt, uint32_t *defer_cnt, int clear_tail,
                                                      const int64_t *row_ids, int64_t row_base, int64_t *out_ids,
                                                      float *out_dist, int32_t *out_counts) {
     extern __shared__ uint64_t s_keys[];
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *c
         const uint32_t m = (uint32_t)s_m;
         cnt[q] = m;
         if (pend_cnt) pend_cnt[q] = 0;  // the re-scorer has consumed this chunk's survivors
+        if (defer_cnt) defer_cnt[q] = 0;  // ... and the deferred pass the parked pairs
         thr_key[q] = s_kth;
         float tf = __int_as_float(0x7f800000);
         if (s_kth != KEY_MAX) tf = filter_threshold(fs, unordered_bits((uint32_t)(s_kth >> 32)), q_mag_f[q]);
@@ -463,7 +470,7 @@ int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int 
 
 int launch_reset_state(Workspace &ws, int nq, cudaStream_t s) {
     reset_state_kernel<<<(nq + 255) / 256 > 0 ? (nq + 255) / 256 : 1, 256, 0, s>>>(ws.d_cnt, ws.d_thr_key, ws.d_thr_f,
-                                                                                  ws.d_status, nq, ws.d_pend_cnt);
+                                                                                  ws.d_status, nq, ws.d_pend_cnt, ws.d_defer_cnt);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }
@@ -474,13 +481,14 @@ int launch_reset_status(Workspace &ws, cudaStream_t s) {
     return PKV_OK;
 }
 
-int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, int64_t *d_ids,
-                  float *d_dist, int32_t *d_counts, cudaStream_t s) {
+int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, bool clear_deferred,
+                  int64_t *d_ids, float *d_dist, int32_t *d_counts, cudaStream_t s) {
     if (nq <= 0) return PKV_OK;
     const size_t smem = (size_t)ws.cap * sizeof(uint64_t);
     PKV_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_kernel<<<nq, 512, smem, s>>>(ws.d_cand, ws.d_cnt, ws.d_thr_key, ws.d_thr_f, ws.d_q_mag_f, ws.d_status,
-                                        (uint32_t)ws.cap, k, fs, ws.d_pend_cnt, clear_tail ? 1 : 0, ix.d_ids,
+                                        (uint32_t)ws.cap, k, fs, ws.d_pend_cnt, clear_deferred ? ws.d_defer_cnt : nullptr,
+                                        clear_tail ? 1 : 0, ix.d_ids,
                                         ix.row_base, d_ids, d_dist, d_counts);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;

@@ -20,6 +20,7 @@ def _same(a, b):
 
 def _f32_index(x):
     ix = pk.VectorIndex(x.shape[1], pk.F32)
+    ix.set_option("live", 2)   # live whenever the kernels can (the default waits for corpora of millions of rows)
     ix.append(x)
     ix.seal()
     return ix
@@ -27,6 +28,7 @@ def _f32_index(x):
 
 def _i8_index(xc, scale):
     ix = pk.VectorIndex(xc.shape[1], pk.I8)
+    ix.set_option("live", 2)
     ix.set_scale_artifact(pk.scale_artifact(scale))
     ix.append(xc)
     ix.seal()
@@ -43,16 +45,17 @@ def test_live_f32_equals_chunked_and_oracle(metric, nq):
         c1 = ix.counters()
         assert c1.last_scan_kind == 8
         assert c1.fallback_queries == c0.fallback_queries, "the live launch overflowed on benign data"
-        # prep, reset, bootstrap scan, select, query codes, ONE scan launch (per <= 1024 queries), select
-        assert c1.kernel_launches - c0.kernel_launches <= 8
-        assert c1.scan_launches - c0.scan_launches <= 3   # bootstrap chunk, query codes, the live scan
+        assert c1.rescored_pairs > c0.rescored_pairs, "the scan kernel's own warps re-scored nothing"
+        ix.set_option("live_start_rows", 4096)   # live right behind the bootstrap chunk: the hardest start
+        early = ix.search(q, 100, metric)
         ix.set_option("live", 0)
         chunked = ix.search(q, 100, metric)
-        assert ix.counters().scan_launches - c1.scan_launches > 3
-        ix.set_option("img8_fused", 0)   # round-1 shape: pend lists + the separate re-score kernel
-        unfused = ix.search(q, 100, metric)
+        ix.set_option("img8_fused", 2)   # every chunk re-scored in-kernel
+        fused = ix.search(q, 100, metric)
+        unfused = chunked
     assert _same(live, chunked), "live and chunked schedules disagree"
-    assert _same(live, unfused), "in-kernel and separate re-scoring disagree"
+    assert _same(early, chunked), "an early live start changed the result"
+    assert _same(fused, unfused), "in-kernel and separate re-scoring disagree"
     assert_close_topk(live, orc.topk(x, q, metric, 100, threads=16), x, q, metric)
 
 
@@ -66,9 +69,12 @@ def test_live_int8_bit_exact(metric, nq):
         c1 = ix.counters()
         assert c1.last_scan_kind == 3
         assert c1.fallback_queries == c0.fallback_queries
+        ix.set_option("live_start_rows", 4096)
+        early = ix.search(qc, 100, metric)
         ix.set_option("live", 0)
         chunked = ix.search(qc, 100, metric)
     assert _same(live, chunked)
+    assert _same(early, chunked)
     assert_exact(live, orc.topk(xc, qc, metric, 100, threads=16))
 
 
@@ -91,6 +97,7 @@ def test_live_ties_and_duplicates():
     xc = np.ascontiguousarray(np.tile(base, (3000, 1)))
     qc = base[:3].copy()
     with pk.VectorIndex(64, pk.I8) as ix:
+        ix.set_option("live", 2)
         ix.append(xc)
         ix.seal()
         for metric in (pk.COSINE, pk.L2):
@@ -139,12 +146,12 @@ def test_f16_index_live_rescoring():
     x = orc.synthetic(100_000, 512, 361).astype(np.float16)
     q = orc.synthetic(300, 512, 362).astype(np.float16)
     with pk.VectorIndex(512, pk.F16) as ix:
+        ix.set_option("live", 2)
         ix.append(x)
         ix.seal()
         live = ix.search(q, 100, pk.COSINE)
         assert ix.counters().last_scan_kind == 8
         ix.set_option("live", 0)
-        ix.set_option("img8_fused", 0)
         old = ix.search(q, 100, pk.COSINE)
     assert _same(live, old)
     xf, qf = x.astype(np.float32), q.astype(np.float32)
