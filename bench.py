@@ -285,12 +285,16 @@ def main():
     out_dev = (torch.empty((a.batch, a.k), dtype=torch.int64, device=dev),
                torch.empty((a.batch, a.k), dtype=torch.float32, device=dev),
                torch.empty(a.batch, dtype=torch.int32, device=dev))
+    comm = None
     if world > 1:
         merged_out = (torch.empty((a.batch, a.k), dtype=torch.int64, device=dev),
                       torch.empty((a.batch, a.k), dtype=torch.float32, device=dev),
                       torch.empty(a.batch, dtype=torch.int32, device=dev))
-        packed = torch.empty((a.batch, a.k, 3), dtype=torch.int32, device=dev)       # ids(2 words) + dist
-        g_packed = torch.empty((world, a.batch, a.k, 3), dtype=torch.int32, device=dev)
+        # the exchange lives in libpkv.so (pkv_comm_* / pkv_search_sharded_device: scan + pack + ONE ncclAllGather +
+        # merge on one stream); torch.distributed only carries the 128-byte NCCL id and the timing barriers
+        uid = torch.tensor(list(pk.Comm.unique_id()) if rank == 0 else [0] * 128, dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        comm = pk.Comm(local_rank, rank, world, bytes(uid.cpu().numpy().tolist()))
 
     merge_launches = [0]
     # config 5: membership bits over this shard's rows (Bernoulli(p), seed 0x5EED+2 over GLOBAL rows: SURVEY 8d),
@@ -304,15 +308,12 @@ def main():
         bm_dev = torch.from_numpy(bm_host.view(np.int64)).to(dev)
 
     def step_device(q):
-        ids, dst, cnt = ix.search(q, a.k, metric_code, out=out_dev, bitmap=bm_dev)
         if world == 1:
-            return ids, dst, cnt
+            return ix.search(q, a.k, metric_code, out=out_dev, bitmap=bm_dev)
         # ONE all-gather of the per-shard candidates: a pack kernel (12-byte entries), the collective, and a merge
-        # kernel that reads the gathered buffer directly - three stream operations per step
-        pk.pack_topk(ids, dst, out=packed, device=local_rank)
-        dist.all_gather_into_tensor(g_packed, packed)
+        # kernel that reads the gathered buffer directly - all inside the library call
         merge_launches[0] += 2
-        return pk.merge_packed(g_packed, out=merged_out, device=local_rank)
+        return comm.search(ix, q, a.k, metric_code, bitmap=bm_dev, out=merged_out)
 
     def barrier():
         if world > 1:
@@ -376,6 +377,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            comm.close()
             dist.destroy_process_group()
         return
 
@@ -465,7 +467,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "pkv_search (C ABI, host buffers)" if world == 1 else
-                       "H2D + pkv_search_device + all_gather + pkv_merge_topk_device + D2H"},
+                       "H2D + pkv_search_sharded_device (scan + pack + ncclAllGather + merge in libpkv.so) + D2H"},
         "gpu_launches": int(c1.kernel_launches - c0.kernel_launches) + merge_launches[0],
         "roofline": roofline,
         "overflow_rescans": int(c1.fallback_queries - c0.fallback_queries),
@@ -553,6 +555,7 @@ def main():
         sub.close()
     print(json.dumps(line), flush=True)
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

@@ -224,6 +224,59 @@ int pkv_pack_topk_device(int device, const int64_t *d_ids, const float *d_dist, 
 int pkv_merge_packed_device(int device, const void *d_packed, int parts, int nq, int k, int64_t *d_out_ids,
                             float *d_out_dist, int32_t *d_out_counts, void *stream);
 
+/* -- sharding: the corpus row-sharded over the GPUs of one box (the reference has no multi-device path) ----
+ * Contiguous row ranges by insertion order, one shard per listed device; every shard scans for the same batch and the
+ * per-shard top-k lists are merged under the same total order (distance, then global row).  Two shapes:
+ *
+ * (1) ONE process, S shards - what the single-process Rust server binds.  pkv_sharded_search is a drop-in for
+ *     pkv_search: host buffers in, global top-k out; the per-shard scans run concurrently, the lists are gathered on the
+ *     first device and merged by the merge kernel.  The same device may be listed several times (tests). */
+typedef struct pkv_sharded pkv_sharded;
+int pkv_sharded_create(const int *devices, int n_shards, int dim, int dtype, pkv_sharded **out);
+int pkv_sharded_destroy(pkv_sharded *h);
+int pkv_sharded_shard_count(const pkv_sharded *h);
+/* Borrows shard i (options, counters, info); the handle stays owned by the sharded index. */
+int pkv_sharded_shard(pkv_sharded *h, int i, pkv_index **out);
+/* Fixes the shard boundaries: ceil(total_rows / S) rows per shard, rounded up to a multiple of 64 so that a global
+ * membership bitmap slices on word boundaries; shard i reports rows i*per .. as its ids (or the appended row_ids). */
+int pkv_sharded_reserve(pkv_sharded *h, int64_t total_rows);
+/* Appends in global insertion order; rows spill over into the next shard at the boundary. */
+int pkv_sharded_append(pkv_sharded *h, const void *rows, const int64_t *row_ids, int64_t n);
+int pkv_sharded_set_scale(pkv_sharded *h, const uint8_t *artifact, size_t len);
+int pkv_sharded_set_option(pkv_sharded *h, const char *name, int64_t value);
+int pkv_sharded_seal(pkv_sharded *h);
+int pkv_sharded_rows(const pkv_sharded *h, int64_t *rows);
+/* As pkv_search.  params->bitmap: ONE bitmap over the global rows (bitmap_stride_words must be 0). */
+int pkv_sharded_search(pkv_sharded *h, const void *queries, int nq, const pkv_search_params *params, int64_t *out_ids,
+                       float *out_dist, int32_t *out_counts);
+
+/* (2) ONE process per GPU (torchrun / MPI style): a communicator over NCCL, resolved at run time (dlopen of
+ *     libnccl.so.2; PKV_ERR_UNSUPPORTED when absent).  Rank 0 makes the 128-byte id, the host distributes it (a file,
+ *     an env var, a torch.distributed broadcast), every rank calls pkv_comm_create. */
+typedef struct pkv_comm pkv_comm;
+int pkv_comm_unique_id(uint8_t *out, size_t len /* 128 */);
+int pkv_comm_create(int device, int rank, int nranks, const uint8_t *unique_id, size_t len /* 128 */, pkv_comm **out);
+int pkv_comm_destroy(pkv_comm *h);
+int pkv_comm_info(const pkv_comm *h, int *rank, int *nranks);
+/* Every rank calls this with ITS shard and the SAME queries (device buffers); on return every rank holds the global
+ * top-k.  The exchange is ONE ncclAllGather of the packed per-shard lists (nq*k*12 bytes per rank) enqueued behind the
+ * scan on `stream`, then the merge kernel reading the gathered buffer.  Collective: all ranks, same order. */
+int pkv_search_sharded_device(pkv_index *shard, pkv_comm *comm, const void *d_queries, int nq,
+                              const pkv_search_params *params, int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts,
+                              void *stream);
+
+/* -- SQLite seam (db/sql_functions.rs:105-128 registers sqlite-vec the same way) ---------------------------------------
+ * sqlite3_pkv_init is an extension entry point - int(sqlite3*, char**, const sqlite3_api_routines*) - to hand to
+ * sqlite3_auto_extension() next to / instead of sqlite3_vec_init, or to load_extension().  Every connection then has
+ *   pkv_topk(model, query_blob, k [, metric])  table-valued: rows (id = item_data.id, d = distance, rank), best first -
+ *                                              substitutable for the `dist_{cte}` CTE of
+ *                                              builder/filters/exact.rs:106-165 truncated to retrieval depth k
+ *   pkv_version(), pkv_scale_from_absmax(x), pkv_last_execute_ms()
+ * `model` (the setter name the filter compilers bind, image_embeddings.rs:140-199) selects an index the host registered
+ * with pkv_sqlite_register_index (NULL handle = withdraw).  The index stays owned by the caller. */
+int pkv_sqlite_register_index(const char *model, pkv_index *h);
+int sqlite3_pkv_init(void *db, char **pzErrMsg, const void *pApi);
+
 /* Per-item aggregation of row distances (builder/filters/exact.rs:67-80):
  * agg 0 MIN / 1 MAX / 2 AVG of d grouped by item, or SUM(d*w)/SUM(w) when d_weights
  * is non-NULL.  item ids are dense 0..n_items-1; NaN rows are skipped (SQL NULL);

@@ -93,6 +93,23 @@ SIGNATURES = {
     "pkv_merge_topk_device": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pkv_pack_topk_device": (C.c_int, [C.c_int, _P, _P, C.c_int64, _P, _P]),
     "pkv_merge_packed_device": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pkv_sharded_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "pkv_sharded_destroy": (C.c_int, [_P]),
+    "pkv_sharded_shard_count": (C.c_int, [_P]),
+    "pkv_sharded_shard": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "pkv_sharded_reserve": (C.c_int, [_P, C.c_int64]),
+    "pkv_sharded_append": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "pkv_sharded_set_scale": (C.c_int, [_P, _P, C.c_size_t]),
+    "pkv_sharded_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "pkv_sharded_seal": (C.c_int, [_P]),
+    "pkv_sharded_rows": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "pkv_sharded_search": (C.c_int, [_P, _P, C.c_int, C.POINTER(SearchParams), _P, _P, _P]),
+    "pkv_comm_unique_id": (C.c_int, [_P, C.c_size_t]),
+    "pkv_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(_P)]),
+    "pkv_comm_destroy": (C.c_int, [_P]),
+    "pkv_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pkv_search_sharded_device": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(SearchParams), _P, _P, _P, _P]),
+    "pkv_sqlite_register_index": (C.c_int, [C.c_char_p, _P]),
     "pkv_aggregate_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "pkv_index_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "pkv_index_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),

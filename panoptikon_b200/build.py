@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall",
-    "-shared", "-cudart", "static", "--threads", "0",
+    "-shared", "-cudart", "static", "--threads", "0", "-ldl",
 ]
 
 

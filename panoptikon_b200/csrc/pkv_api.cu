@@ -56,9 +56,6 @@ int DeviceGuard::use(int device) {
 DeviceGuard::~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
 }
-#define PKV_USE_DEVICE(dev) \
-    ::pkv::DeviceGuard _device_guard; \
-    PKV_TRY(_device_guard.use(dev))
 
 // figures of the last search issued by the calling thread (pkv_counters.last_*)
 struct LastSearch {

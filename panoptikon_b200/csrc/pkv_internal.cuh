@@ -53,6 +53,9 @@ struct DeviceGuard {  // pkv_api.cu
     int use(int device);
     ~DeviceGuard();
 };
+#define PKV_USE_DEVICE(dev)           \
+    ::pkv::DeviceGuard _device_guard; \
+    PKV_TRY(_device_guard.use(dev))
 
 // ------------------------------------------------------------- key packing
 // Total order of the contract: ascending f32 distance, NaN last, ties by ascending row.

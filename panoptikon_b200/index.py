@@ -213,6 +213,130 @@ class VectorIndex:
         return ids, dist, counts
 
 
+class ShardedIndex:
+    """The corpus row-sharded over GPUs inside ONE process (pkv_sharded_*): contiguous row ranges in insertion
+    order, one shard per listed device, per-shard scans run concurrently, lists merged on the first device."""
+
+    def __init__(self, dim: int, dtype: int = N.F32, devices=(0,), total_rows: int = 0):
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        N.check(N.lib().pkv_sharded_create(devs, len(devices), dim, dtype, C.byref(self._h)))
+        self.dim, self.dtype, self.devices = dim, dtype, tuple(devices)
+        if total_rows:
+            self.reserve(total_rows)
+
+    def close(self) -> None:
+        if self._h:
+            N.lib().pkv_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reserve(self, total_rows: int) -> None:
+        N.check(N.lib().pkv_sharded_reserve(self._h, total_rows))
+
+    def append(self, rows, row_ids=None) -> None:
+        rows = np.ascontiguousarray(rows, dtype=_NP[self.dtype])
+        assert rows.ndim == 2 and rows.shape[1] == self.dim
+        ids = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.int64)
+        N.check(N.lib().pkv_sharded_append(self._h, _np_ptr(rows), _np_ptr(ids), rows.shape[0]))
+
+    def set_scale_artifact(self, artifact: bytes) -> None:
+        buf = (C.c_uint8 * max(len(artifact), 1)).from_buffer_copy(artifact.ljust(1, b"\0"))
+        N.check(N.lib().pkv_sharded_set_scale(self._h, buf, len(artifact)))
+
+    def set_option(self, name: str, value: int) -> None:
+        N.check(N.lib().pkv_sharded_set_option(self._h, name.encode(), value))
+
+    def seal(self) -> None:
+        N.check(N.lib().pkv_sharded_seal(self._h))
+
+    @property
+    def rows(self) -> int:
+        out = C.c_int64()
+        N.check(N.lib().pkv_sharded_rows(self._h, C.byref(out)))
+        return int(out.value)
+
+    def shard_rows(self):
+        out = []
+        for i in range(N.lib().pkv_sharded_shard_count(self._h)):
+            h = C.c_void_p()
+            N.check(N.lib().pkv_sharded_shard(self._h, i, C.byref(h)))
+            info = N.IndexInfo()
+            N.check(N.lib().pkv_index_get_info(h, C.byref(info)))
+            out.append(int(info.rows))
+        return out
+
+    def search(self, queries: np.ndarray, k: int, metric: int = N.COSINE, bitmap=None):
+        queries = np.ascontiguousarray(queries)
+        if queries.ndim == 1:
+            queries = queries[None, :]
+        if queries.shape[1] != self.dim:
+            raise N.PkvError(N.ERR_DIM_MISMATCH, f"query dimension {queries.shape[1]} != index dimension {self.dim}")
+        nq = queries.shape[0]
+        p = N.SearchParams(metric=metric, k=k, query_dtype=_CODE[queries.dtype])
+        if bitmap is not None:
+            bitmap = np.ascontiguousarray(bitmap, dtype=np.uint64)
+            p.bitmap = bitmap.ctypes.data
+        ids = np.empty((nq, max(k, 1)), np.int64)
+        dist = np.empty((nq, max(k, 1)), np.float32)
+        counts = np.empty(nq, np.int32)
+        N.check(N.lib().pkv_sharded_search(self._h, _np_ptr(queries), nq, C.byref(p), _np_ptr(ids), _np_ptr(dist),
+                                           _np_ptr(counts)))
+        return ids, dist, counts
+
+
+class Comm:
+    """One process per GPU: the library's NCCL communicator (pkv_comm_*).  `unique_id()` on rank 0, distribute the
+    128 bytes by any means, then Comm(device, rank, nranks, uid) on every rank."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        N.check(N.lib().pkv_comm_unique_id(buf, 128))
+        return bytes(buf)
+
+    def __init__(self, device: int, rank: int, nranks: int, uid: bytes):
+        self._h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        N.check(N.lib().pkv_comm_create(device, rank, nranks, buf, 128, C.byref(self._h)))
+        self.rank, self.nranks = rank, nranks
+
+    def close(self) -> None:
+        if self._h:
+            N.lib().pkv_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def search(self, index: "VectorIndex", queries, k: int, metric: int = N.COSINE, bitmap=None, out=None):
+        """Every rank: its shard + the same torch CUDA queries -> the global top-k (CUDA tensors) on every rank."""
+        import torch
+
+        assert queries.is_cuda and queries.is_contiguous() and queries.dim() == 2
+        nq = queries.shape[0]
+        p = N.SearchParams(metric=metric, k=k, query_dtype=_torch_code(queries))
+        if bitmap is not None:
+            p.bitmap = bitmap.data_ptr()
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.int64, device=queries.device),
+                   torch.empty((nq, k), dtype=torch.float32, device=queries.device),
+                   torch.empty(nq, dtype=torch.int32, device=queries.device))
+        stream = torch.cuda.current_stream(queries.device).cuda_stream
+        N.check(N.lib().pkv_search_sharded_device(index._h, self._h, C.c_void_p(queries.data_ptr()), nq, C.byref(p),
+                                                  C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                                  C.c_void_p(out[2].data_ptr()), C.c_void_p(stream)))
+        return out
+
+
 # ---- codec (db/vector_quants.rs:1446-1503) -------------------------------------
 
 def scale_from_absmax(absmax: float) -> float:

@@ -4,6 +4,7 @@ import pytest
 
 import panoptikon_b200 as pk
 from oracle import oracle as orc
+from panoptikon_b200 import _native as N
 from tests.helpers import assert_close_topk, assert_exact, int8_space
 
 pytestmark = pytest.mark.gpu
@@ -231,3 +232,50 @@ def test_similar_to_matches_reference_fixture_and_oracle():
             assert cnt == 50 and 42 not in got
             assert np.allclose(vals.cpu().numpy()[:cnt], a[order[:50]], rtol=2e-5, atol=1e-6)
             assert len(set(got) ^ set(order[:50])) <= 2
+
+
+def test_sqlite_table_valued_function_joins_like_the_distance_cte():
+    """a15/a16/f4: pkv_topk(...) loaded into SQLite returns the (item_data.id, d) rows of one query, joined the way
+    builder/filters/exact.rs:106-165 joins `embeddings`: per-file MIN(d) + row_number() rank, compared with the same
+    aggregate computed from the oracle's distances."""
+    import sqlite3
+
+    rng = np.random.default_rng(77)
+    n, d = 20_000, 64
+    x, q = orc.synthetic(n, d, 701), orc.synthetic(1, d, 702)
+    data_ids = np.arange(n, dtype=np.int64) * 3 + 11           # item_data.id of every embedding row
+    file_of = rng.integers(0, 4000, size=n)                    # several embeddings per file (video frames, text chunks)
+    con = sqlite3.connect(":memory:")
+    con.enable_load_extension(True)
+    con.load_extension(N.LIB_PATH)
+    con.execute("CREATE TABLE item_data(id INTEGER PRIMARY KEY, file_id INTEGER)")
+    con.executemany("INSERT INTO item_data VALUES (?, ?)", zip(data_ids.tolist(), file_of.tolist()))
+    with pk.VectorIndex(d, pk.F32) as ix:
+        ix.append(x, data_ids)
+        ix.seal()
+        assert N.lib().pkv_sqlite_register_index(b"clip/test", ix._h) == 0
+        try:
+            k = 500
+            rows = con.execute(
+                "WITH dist AS MATERIALIZED (SELECT item_data.file_id AS file_id, t.d AS d "
+                "  FROM pkv_topk('clip/test', ?, ?, 'COSINE') AS t JOIN item_data ON item_data.id = t.id) "
+                "SELECT file_id, MIN(d) AS agg, row_number() OVER (ORDER BY MIN(d) ASC) AS order_rank "
+                "FROM dist GROUP BY file_id ORDER BY order_rank LIMIT 50", (q[0].tobytes(), k)).fetchall()
+            raw = con.execute("SELECT id, d, rank FROM pkv_topk('clip/test', ?, 7)", (q[0].tobytes(),)).fetchall()
+            assert con.execute("SELECT pkv_last_execute_ms()").fetchone()[0] > 0.0
+            with pytest.raises(sqlite3.OperationalError, match="stores 64-dimensional"):
+                con.execute("SELECT id FROM pkv_topk('clip/test', ?, 7)", (q[0, :32].tobytes(),)).fetchall()
+            with pytest.raises(sqlite3.OperationalError, match="k must be a positive integer"):
+                con.execute("SELECT id FROM pkv_topk('clip/test', ?, 0)", (q[0].tobytes(),)).fetchall()
+        finally:
+            N.lib().pkv_sqlite_register_index(b"clip/test", None)
+    want = orc.topk(x, q, orc.COSINE, k, threads=4)
+    best = {}
+    for r, dist in zip(want[0][0], want[1][0]):
+        f = int(file_of[r])
+        best[f] = min(best.get(f, np.inf), float(dist))
+    ranked = sorted(best.items(), key=lambda kv: (kv[1], kv[0]))[:50]
+    assert [r[2] for r in rows] == list(range(1, 51))
+    for (f_got, agg_got, _), (f_want, agg_want) in zip(rows, ranked):
+        assert abs(agg_got - agg_want) <= 1e-5 * max(abs(agg_want), abs(1 - agg_want)) + 1e-7
+    assert [r[0] for r in raw] == data_ids[want[0][0][:7]].tolist() and [r[2] for r in raw] == list(range(1, 8))

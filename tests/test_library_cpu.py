@@ -31,6 +31,34 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in pkv.h but not exported"
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     assert lib.pkv_abi_version() == 1
+    assert hasattr(lib, "sqlite3_pkv_init"), "the SQLite extension entry point is not exported"
+
+
+def test_sqlite_extension_loads_and_registers_functions():
+    """a15: libpkv.so loads into SQLite the way sqlite-vec does (extension entry point), and the table-valued function is
+    planned and reports errors as SQL errors.  Python's stdlib sqlite3 stands in for the Rust server's libsqlite3."""
+    import sqlite3
+
+    con = sqlite3.connect(":memory:")
+    con.enable_load_extension(True)
+    con.load_extension(N.LIB_PATH)   # default entry point of libpkv.so: sqlite3_pkv_init
+    assert con.execute("SELECT pkv_version()").fetchone()[0].startswith("libpkv abi 1")
+    got = con.execute("SELECT pkv_scale_from_absmax(11.0), pkv_scale_from_absmax(0.0), pkv_scale_from_absmax(NULL)").fetchone()
+    assert got[0] == pk.scale_from_absmax(11.0) and got[1] == 1.0 and got[2] is None
+    assert con.execute("SELECT pkv_last_execute_ms()").fetchone()[0] == 0.0
+    blob = np.zeros(8, np.float32).tobytes()
+    with pytest.raises(sqlite3.OperationalError, match="no resident index is registered for setter 'nope'"):
+        con.execute("SELECT id, d FROM pkv_topk('nope', ?, 10)", (blob,)).fetchall()
+    with pytest.raises(sqlite3.OperationalError):
+        con.execute("SELECT id FROM pkv_topk('nope')").fetchall()      # the query blob is mandatory
+    # the plan joins it like a table (the shape of dist_{cte}, exact.rs:106-165)
+    con.execute("CREATE TABLE item_data(id INTEGER PRIMARY KEY, item_id INTEGER)")
+    plan = con.execute("EXPLAIN QUERY PLAN SELECT item_data.item_id, t.d FROM pkv_topk('m', ?, 5, 'cosine') AS t "
+                       "JOIN item_data ON item_data.id = t.id ORDER BY t.d", (blob,)).fetchall()
+    text = " ".join(str(r) for r in plan)
+    assert "VIRTUAL TABLE INDEX 15" in text.upper()          # all four arguments reached xBestIndex
+    assert "USING INTEGER PRIMARY KEY" in text.upper()       # item_data is probed by id, per returned row
+    assert "TEMP B-TREE" not in text.upper()                 # rows arrive best first: ORDER BY d needs no sort
 
 
 def test_host_scalar_codec_matches_reference_kats():
