@@ -198,6 +198,37 @@ typedef struct {
 } pkv_rank_params;
 int pkv_rank_groups_device(pkv_index *h, const void *d_queries, int nq, const pkv_rank_params *params,
                            int64_t *d_out_groups, double *d_out_agg, int32_t *d_out_count, void *stream);
+/* similar_to (pql/builder/filters/item_similarity.rs:83-142 arguments, :432-581 the rendered self-join): the stored
+ * vectors of the TARGET item are the query side ("main_embeddings"), every other stored row a candidate
+ * ("other_embeddings"); AGG(d) - or SUM(d*w)/SUM(w) with w = pow(conf_m*conf_o, wc) * pow(lang_m*lang_o, wl), which
+ * factorises into a per-row weight on each side - runs over every admitted (target vector, candidate vector) pair,
+ * grouped by the candidate's group (file / data row), ranked ascending.
+ *   d_target_rows : positions of the target item's rows in this index (they are read on the device: no host copy)
+ *   d_group_of_row: dense group per stored row, -1 = not a candidate; the caller gives the target item's own rows -1
+ *                   (`other.sha256 != target`)
+ *   d_modality    : per stored row 0 = image setter ("clip"), 1 = its "t"-prefixed text sibling ("text-embedding");
+ *                   one index holds the whole space (db/vector_quants.rs:480-510).  NULL = a plain single-setter index.
+ *   clip_xmodal=0 : only image rows take part on either side; =1: all pairs except image-image when !xmodal_i2i and
+ *                   text-text when !xmodal_t2t (:468-488)
+ *   d_weights     : per stored row pow(coalesce(conf,1),wc)*pow(coalesce(lang_conf,1),wl), or NULL */
+typedef struct {
+    int32_t metric;       /* PKV_L2 (the default of SimilarityArgs) or PKV_COSINE */
+    int32_t aggregation;  /* pkv_distance_aggregation; similar_to defaults to AVG */
+    int32_t offset;
+    int32_t limit;
+    int32_t clip_xmodal;
+    int32_t xmodal_i2i;
+    int32_t xmodal_t2t;
+    int32_t n_targets;
+    const int64_t *d_target_rows;
+    const int64_t *d_group_of_row;
+    int64_t n_groups;
+    const uint8_t *d_modality;
+    const float *d_weights;
+} pkv_similar_params;
+int pkv_similar_to_device(pkv_index *h, const pkv_similar_params *params, int64_t *d_out_groups, double *d_out_agg,
+                          int32_t *d_out_count, void *stream);
+
 /* Copies stored rows (by position) into d_out[n][dim] in the index dtype: similar_to reads the target's
  * own stored vectors as its queries (item_similarity.rs:352-426). */
 int pkv_index_get_rows_device(pkv_index *h, const int64_t *d_rows, int n, void *d_out, void *stream);
@@ -358,6 +389,23 @@ int pkv_space_set_quant(pkv_space *s, const char *profile_name, int is_default, 
 int pkv_space_search(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
                      const char *variant_or_null, int64_t k_arg, int depth, int64_t *out_ids, float *out_dist,
                      int32_t *out_counts, int64_t *used_profile_id);
+
+/* -- cross-modal spaces (db/vector_quants.rs:480-510; image_embeddings.rs:140-199) -------------------------------------
+ * A CLIP image setter and its "t"-prefixed text sibling form ONE space with one int8 scale; a filter without
+ * clip_xmodal sees the image setter's rows only, with it both setters' rows.  One index holds the whole space. */
+/* xmodal_text_sibling_name (db/vector_quants.rs:51-53): "t" + model. */
+int pkv_xmodal_text_sibling_name(const char *model, char *out, size_t cap);
+/* The loop of resolve_ready_pair (db/vector_quants.rs:1817-1867) over the setters a query involves.  states[i]:
+ * 0 no such setter (skipped), 1 ready (pairs[i] valid), 2 exists but not ready.  PKV_OK + *out, or PKV_ERR_NOT_READY
+ * (a setter not ready, or siblings that do not share scale and dim: "a rebuild is pending"). */
+int pkv_resolve_ready_pair(const pkv_ready_pair *pairs, const int32_t *states, int n, pkv_ready_pair *out);
+/* Per stored row of the space's indexes (same row order in the exact and the quant index): 0 image setter, 1 text
+ * sibling.  HOST array; NULL withdraws it (single-setter space). */
+int pkv_space_set_modality(pkv_space *s, const uint8_t *row_modality, int64_t n_rows);
+/* pkv_space_search with SemanticImageArgs.clip_xmodal (image_embeddings.rs:21-83): 0 = the image setter's rows only. */
+int pkv_space_search_xmodal(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
+                            const char *variant_or_null, int64_t k_arg, int depth, int clip_xmodal, int64_t *out_ids,
+                            float *out_dist, int32_t *out_counts, int64_t *used_profile_id);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ from ._native import (AGG_AVG, AGG_MAX, AGG_MIN, COSINE, DEFAULT_K, DOT, F16, F3
 from .index import (Comm, ShardedIndex, VectorIndex, aggregate, artifact_scale, blob_absmax, fuse_ranks, merge_packed, merge_topk, pack_topk, quantize_int8,
                     scale_artifact, scale_from_absmax)
 from .pql import (PqlError, ReadyPair, Space, parse_distance_aggregation, parse_distance_function, parse_index_mode,
-                  quant_requested, quant_strict, similar_to, validate_quant_args)
+                  quant_requested, quant_strict, resolve_ready_pair, similar_to, validate_quant_args,
+                  xmodal_text_sibling_name)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -58,6 +58,15 @@ class RankParams(C.Structure):
     ]
 
 
+class SimilarParams(C.Structure):
+    _fields_ = [
+        ("metric", C.c_int32), ("aggregation", C.c_int32), ("offset", C.c_int32), ("limit", C.c_int32),
+        ("clip_xmodal", C.c_int32), ("xmodal_i2i", C.c_int32), ("xmodal_t2t", C.c_int32), ("n_targets", C.c_int32),
+        ("d_target_rows", C.c_void_p), ("d_group_of_row", C.c_void_p), ("n_groups", C.c_int64),
+        ("d_modality", C.c_void_p), ("d_weights", C.c_void_p),
+    ]
+
+
 class ReadyPair(C.Structure):
     _fields_ = [("profile_id", C.c_int64), ("scale", C.c_float), ("dim", C.c_int64)]
 
@@ -109,6 +118,12 @@ SIGNATURES = {
     "pkv_comm_destroy": (C.c_int, [_P]),
     "pkv_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pkv_search_sharded_device": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(SearchParams), _P, _P, _P, _P]),
+    "pkv_similar_to_device": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "pkv_xmodal_text_sibling_name": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
+    "pkv_resolve_ready_pair": (C.c_int, [_P, _P, C.c_int, _P]),
+    "pkv_space_set_modality": (C.c_int, [_P, _P, C.c_int64]),
+    "pkv_space_search_xmodal": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64, C.c_int,
+                                          C.c_int, _P, _P, _P, C.POINTER(C.c_int64)]),
     "pkv_sqlite_register_index": (C.c_int, [C.c_char_p, _P]),
     "pkv_aggregate_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "pkv_index_counters": (C.c_int, [_P, C.POINTER(Counters)]),

@@ -1144,6 +1144,62 @@ int pkv_rank_groups_device(pkv_index *h, const void *d_queries, int nq, const pk
     return PKV_OK;
 }
 
+// similar_to (item_similarity.rs:432-581): the target item's own stored vectors are the queries; AGG runs over every
+// (target vector, candidate vector) pair the xmodal rules admit.
+int pkv_similar_to_device(pkv_index *h, const pkv_similar_params *p, int64_t *d_out_groups, double *d_out_agg,
+                          int32_t *d_out_count, void *stream) {
+    if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
+    if (!p) return fail(PKV_ERR_INVALID, "similar_to params are NULL");
+    Index &ix = *reinterpret_cast<Index *>(h);
+    PKV_USE_DEVICE(ix.device);
+    if (p->n_targets < 1 || !p->d_target_rows) return fail(PKV_ERR_INVALID, "the target item has no stored vectors");
+    if (p->limit < 1 || p->offset < 0 || p->offset + p->limit > 2048)
+        return fail(PKV_ERR_INVALID, "need limit >= 1, offset >= 0 and offset + limit <= 2048");
+    if (p->aggregation < PKV_AGG_MIN || p->aggregation > PKV_AGG_AVG) return fail(PKV_ERR_INVALID, "unknown aggregation");
+    if (p->metric != PKV_L2 && p->metric != PKV_COSINE) return fail(PKV_ERR_INVALID, "distance function must be L2 or COSINE");
+    if (p->n_groups < 0 || p->n_groups >= 0xFFFFFFFFll) return fail(PKV_ERR_INVALID, "n_groups out of range");
+    if (!p->d_group_of_row || !d_out_groups || !d_out_agg || !d_out_count) return fail(PKV_ERR_INVALID, "NULL buffer");
+    if (p->clip_xmodal && !p->d_modality)
+        return fail(PKV_ERR_INVALID, "clip_xmodal needs the per-row modality of the space (image setter / text sibling)");
+    const int64_t rows = ix.sealed_rows;
+    const int T = p->n_targets;
+    if ((double)rows * T > 4.0e9)
+        return fail(PKV_ERR_UNSUPPORTED, "%d target vectors x %lld rows exceeds the dense scoring buffer", T, (long long)rows);
+    cudaStream_t s = (cudaStream_t)stream;
+    void *d_q = nullptr;
+    float *d_dist = nullptr, *d_qw = nullptr;
+    uint8_t *d_qm = nullptr;
+    PKV_CUDA(cudaMallocAsync(&d_q, (size_t)T * ix.dim * ix.elem, s));
+    PKV_CUDA(cudaMallocAsync((void **)&d_dist, sizeof(float) * (size_t)(rows > 0 ? rows : 1) * T, s));
+    PKV_CUDA(cudaMallocAsync((void **)&d_qw, sizeof(float) * T, s));
+    PKV_CUDA(cudaMallocAsync((void **)&d_qm, (size_t)T, s));
+    int st;
+    {
+        std::shared_lock<std::shared_mutex> lock(ix.mu);
+        st = launch_gather_rows(ix, p->d_target_rows, T, d_q, s);
+    }
+    if (st == PKV_OK) st = launch_gather_attrs(p->d_target_rows, T, rows, p->d_modality, p->d_weights, d_qm, d_qw, s);
+    if (st == PKV_OK && rows > 0) st = pkv_distances_device(h, d_q, T, p->metric, ix.dtype, d_dist, stream);
+    if (st == PKV_OK) {
+        PairRules rules;
+        rules.row_modality = p->d_modality;
+        rules.q_modality = d_qm;
+        rules.q_weights = p->d_weights ? d_qw : nullptr;
+        rules.clip_xmodal = p->clip_xmodal ? 1 : 0;
+        rules.skip_i2i = (p->clip_xmodal && !p->xmodal_i2i) ? 1 : 0;
+        rules.skip_t2t = (p->clip_xmodal && !p->xmodal_t2t) ? 1 : 0;
+        st = rank_groups(d_dist, rows, T, p->d_group_of_row, p->d_weights, p->n_groups, p->aggregation, p->offset, p->limit,
+                         d_out_groups, d_out_agg, d_out_count, s, &rules);
+    }
+    cudaFreeAsync(d_q, s);
+    cudaFreeAsync(d_dist, s);
+    cudaFreeAsync(d_qw, s);
+    cudaFreeAsync(d_qm, s);
+    if (st != PKV_OK) return st;
+    PKV_CUDA(cudaStreamSynchronize(s));
+    return PKV_OK;
+}
+
 int pkv_index_get_rows_device(pkv_index *h, const int64_t *d_rows, int n, void *d_out, void *stream) {
     if (!h) return fail(PKV_ERR_INVALID, "index handle is NULL");
     Index &ix = *reinterpret_cast<Index *>(h);

@@ -328,9 +328,17 @@ int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStre
 int launch_rescore_deferred(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s);
 
 // pkv_operator.cu
+struct PairRules {  // which (target row, candidate row) pairs of similar_to's self-join take part, and the target-side weight
+    const uint8_t *row_modality;  // per stored row: 0 image ("clip"), 1 text ("text-embedding"); NULL = no rules
+    const uint8_t *q_modality;    // per target row
+    const float *q_weights;       // per target row, or NULL
+    int clip_xmodal, skip_i2i, skip_t2t;
+};
 int rank_groups(const float *d_dist, int64_t rows, int nq, const int64_t *d_group_of_row, const float *d_weights,
                 int64_t n_groups, int agg, int offset, int limit, int64_t *d_out_groups, double *d_out_agg,
-                int32_t *d_out_count, cudaStream_t s);
+                int32_t *d_out_count, cudaStream_t s, const PairRules *rules_or_null = nullptr);
+int launch_gather_attrs(const int64_t *d_rows, int n, int64_t n_rows, const uint8_t *d_modality, const float *d_weights,
+                        uint8_t *d_q_mod, float *d_q_w, cudaStream_t s);
 int launch_gather_rows(const Index &ix, const int64_t *d_rows, int n, void *d_out, cudaStream_t s);
 // pkv_topk.cu
 int launch_reset_status(Workspace &ws, cudaStream_t s);

@@ -46,18 +46,29 @@ __global__ void grp_init_kernel(double *acc, double *den, uint32_t *valid, uint3
 // one thread per (query, row) pair of a [nq][rows] distance block
 __global__ void grp_accum_kernel(const float *dist, int64_t rows, int nq, const int64_t *group_of_row, const float *w,
                                  int64_t n_groups, int agg, double *acc, double *den, uint32_t *valid,
-                                 uint32_t *present) {
+                                 uint32_t *present, const PairRules rules) {
     const int64_t total = rows * nq;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i % rows;
         const int64_t g = group_of_row[r];
         if (g < 0 || g >= n_groups) continue;  // not a candidate (context filter, the similar_to target itself)
+        const int64_t qi = i / rows;
+        if (rules.row_modality) {
+            // similar_to's pair rules (item_similarity.rs:468-488): without clip_xmodal only the image setter's rows
+            // exist on either side; with it, image-image pairs go when !xmodal_i2i, text-text pairs when !xmodal_t2t
+            const int rm = rules.row_modality[r], qm = rules.q_modality[qi];
+            if (!rules.clip_xmodal && (rm != 0 || qm != 0)) continue;
+            if (rules.skip_i2i && rm == 0 && qm == 0) continue;
+            if (rules.skip_t2t && rm == 1 && qm == 1) continue;
+        }
         present[g] = 1;
         const float df = dist[i];
         if (df != df) continue;  // SQL NULL is skipped by every aggregate
         const double d = (double)df;
         if (w) {
-            const double ww = (double)w[r];
+            // pow(conf_main * conf_other, wc) * pow(lang_main * lang_other, wl) factorises into a per-row and a
+            // per-target weight (item_similarity.rs:523-560)
+            const double ww = (double)w[r] * (rules.q_weights ? (double)rules.q_weights[qi] : 1.0);
             atomicAdd(acc + g, d * ww);
             atomicAdd(den + g, ww);
         } else if (agg == PKV_AGG_AVG) {
@@ -168,7 +179,10 @@ __global__ void rank_emit_kernel(const uint64_t *keys, const uint32_t *ids, int 
 // dist: [nq][rows] on the device.  Ranks groups and writes `limit` entries starting at `offset`.
 int rank_groups(const float *d_dist, int64_t rows, int nq, const int64_t *d_group_of_row, const float *d_weights,
                 int64_t n_groups, int agg, int offset, int limit, int64_t *d_out_groups, double *d_out_agg,
-                int32_t *d_out_count, cudaStream_t s) {
+                int32_t *d_out_count, cudaStream_t s, const PairRules *rules_or_null) {
+    PairRules rules;
+    memset(&rules, 0, sizeof(rules));
+    if (rules_or_null) rules = *rules_or_null;
     const int keep = offset + limit;
     if (keep > SLICE / 2) return fail(PKV_ERR_INVALID, "offset + limit must not exceed %d", SLICE / 2);
     double *acc = nullptr, *den = nullptr;
@@ -197,7 +211,7 @@ int rank_groups(const float *d_dist, int64_t rows, int nq, const int64_t *d_grou
             int64_t blocks = (total + 255) / 256;
             if (blocks > 148 * 32) blocks = 148 * 32;
             grp_accum_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_dist, rows, nq, d_group_of_row, d_weights, n_groups, agg,
-                                                             acc, den, valid, present);
+                                                             acc, den, valid, present, rules);
         }
         grp_keys_kernel<<<gb, 256, 0, s>>>(acc, den, valid, present, ng, agg, d_weights ? 1 : 0, keys[0], ids[0]);
         int64_t n = ng;
@@ -233,6 +247,25 @@ __global__ void gather_rows_kernel(const uint8_t *data, int64_t pitch, int row_b
     const int64_t src = rows[r];
     for (int i = threadIdx.x; i < row_bytes; i += blockDim.x)
         out[(size_t)r * row_bytes + i] = (src >= 0 && src < n_rows) ? data[(size_t)src * pitch + i] : 0;
+}
+
+// modality and weight of the target's rows (the "main" side of similar_to's self-join)
+__global__ void gather_attrs_kernel(const int64_t *rows, int n, int64_t n_rows, const uint8_t *modality, const float *weights,
+                                    uint8_t *q_mod, float *q_w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = rows[i];
+    const bool ok = r >= 0 && r < n_rows;
+    q_mod[i] = (ok && modality) ? modality[r] : 0;
+    q_w[i] = (ok && weights) ? weights[r] : 1.0f;
+}
+
+int launch_gather_attrs(const int64_t *d_rows, int n, int64_t n_rows, const uint8_t *d_modality, const float *d_weights,
+                        uint8_t *d_q_mod, float *d_q_w, cudaStream_t s) {
+    if (n <= 0) return PKV_OK;
+    gather_attrs_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_rows, n, n_rows, d_modality, d_weights, d_q_mod, d_q_w);
+    PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
 }
 
 int launch_gather_rows(const Index &ix, const int64_t *d_rows, int n, void *d_out, cudaStream_t s) {

@@ -55,6 +55,11 @@ struct pkv_space {
     pkv_index *exact = nullptr;
     std::map<std::string, QuantEntry> profiles;  // name -> ready pair (absent = not ready)
     std::string default_profile;                 // "" = no default configured
+    // cross-modal space (db/vector_quants.rs:480-510): the rows of the image setter and of its "t"-prefixed text
+    // sibling live in ONE index with one scale; image_only marks the image setter's rows (the membership of a filter
+    // without clip_xmodal, image_embeddings.rs:140-199)
+    std::vector<uint64_t> image_only;            // empty = single-setter space (every row is a member)
+    int64_t modality_rows = 0;
     std::mutex mu;
 };
 
@@ -162,10 +167,82 @@ int pkv_space_set_quant(pkv_space *s, const char *profile_name, int is_default, 
     return PKV_OK;
 }
 
-// resolve_vector_quant (preprocess.rs:314-393) followed by the scan the compiled SQL would run.
+// xmodal_text_sibling_name (db/vector_quants.rs:51-53)
+int pkv_xmodal_text_sibling_name(const char *model, char *out, size_t cap) {
+    if (!model || !out) return fail(PKV_ERR_INVALID, "NULL argument");
+    const size_t need = strlen(model) + 2;
+    if (cap < need) return fail(PKV_ERR_INVALID, "buffer too small for the sibling name (%zu bytes needed)", need);
+    out[0] = 't';
+    memcpy(out + 1, model, need - 1);
+    return PKV_OK;
+}
+
+// The loop of resolve_ready_pair (db/vector_quants.rs:1817-1867) over the setters a query involves (the model and,
+// under clip_xmodal, its text sibling).  states[i]: 0 = no such setter (skipped: it contributes nothing), 1 = its
+// coverage row is ready and pairs[i] holds (profile_id, scale, dim), 2 = the setter exists but its pair is not ready.
+// PKV_OK and *out when every existing setter is ready AND all share one scale and dim ("xmodal siblings must share
+// one artifact; a mismatch means a rebuild is pending"); PKV_ERR_NOT_READY otherwise (also when no setter exists).
+int pkv_resolve_ready_pair(const pkv_ready_pair *pairs, const int32_t *states, int n, pkv_ready_pair *out) {
+    if (n < 0 || (n > 0 && (!pairs || !states)) || !out) return fail(PKV_ERR_INVALID, "NULL argument");
+    bool have = false;
+    pkv_ready_pair r{};
+    for (int i = 0; i < n; ++i) {
+        if (states[i] == 0) continue;
+        if (states[i] != 1) return fail(PKV_ERR_NOT_READY, "setter %d of the query has no ready pair", i);
+        const pkv_ready_pair &p = pairs[i];
+        if (!(p.scale > 0.0f) || !(p.scale <= 3.402823466e+38f) || p.dim < 1)
+            return fail(PKV_ERR_NOT_READY, "setter %d has no dimension or no usable scale", i);
+        if (!have) {
+            r = p;
+            have = true;
+        } else if (r.scale != p.scale || r.dim != p.dim) {
+            return fail(PKV_ERR_NOT_READY, "xmodal siblings do not share one artifact (a rebuild is pending)");
+        }
+    }
+    if (!have) return fail(PKV_ERR_NOT_READY, "none of the query's setters exists");
+    *out = r;
+    return PKV_OK;
+}
+
+int pkv_space_set_modality(pkv_space *s, const uint8_t *row_modality, int64_t n_rows) {
+    if (!s) return fail(PKV_ERR_INVALID, "space handle is NULL");
+    std::lock_guard<std::mutex> g(s->mu);
+    if (!row_modality || n_rows <= 0) {
+        s->image_only.clear();
+        s->modality_rows = 0;
+        return PKV_OK;
+    }
+    s->image_only.assign((size_t)((n_rows + 63) / 64), 0ull);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        if (row_modality[r] > 1) return fail(PKV_ERR_INVALID, "row %lld: modality must be 0 (image) or 1 (text)", (long long)r);
+        if (row_modality[r] == 0) s->image_only[(size_t)(r >> 6)] |= 1ull << (r & 63);
+    }
+    s->modality_rows = n_rows;
+    return PKV_OK;
+}
+
+static int space_search(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
+                        const char *variant_or_null, int64_t k_arg, int depth, int clip_xmodal, int64_t *out_ids,
+                        float *out_dist, int32_t *out_counts, int64_t *used_profile_id);
+
 int pkv_space_search(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
                      const char *variant_or_null, int64_t k_arg, int depth, int64_t *out_ids, float *out_dist,
                      int32_t *out_counts, int64_t *used_profile_id) {
+    return space_search(s, queries, nq, query_dim, metric, index_mode, variant_or_null, k_arg, depth, 0, out_ids, out_dist,
+                        out_counts, used_profile_id);
+}
+
+int pkv_space_search_xmodal(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
+                            const char *variant_or_null, int64_t k_arg, int depth, int clip_xmodal, int64_t *out_ids,
+                            float *out_dist, int32_t *out_counts, int64_t *used_profile_id) {
+    return space_search(s, queries, nq, query_dim, metric, index_mode, variant_or_null, k_arg, depth, clip_xmodal ? 1 : 0,
+                        out_ids, out_dist, out_counts, used_profile_id);
+}
+
+// resolve_vector_quant (preprocess.rs:314-393) followed by the scan the compiled SQL would run.
+static int space_search(pkv_space *s, const float *queries, int nq, int query_dim, int metric, int index_mode,
+                        const char *variant_or_null, int64_t k_arg, int depth, int clip_xmodal, int64_t *out_ids,
+                        float *out_dist, int32_t *out_counts, int64_t *used_profile_id) {
     if (!s) return fail(PKV_ERR_INVALID, "space handle is NULL");
     if (used_profile_id) *used_profile_id = -1;
     int st = pkv_validate_quant_args(index_mode, k_arg);
@@ -208,17 +285,34 @@ int pkv_space_search(pkv_space *s, const float *queries, int nq, int query_dim, 
     p.metric = metric;
     p.k = depth > PKV_MAX_K ? PKV_MAX_K : depth;
     p.query_dtype = PKV_F32;
+    // membership (image_embeddings.rs:140-199): the model's own rows, plus its text sibling's under clip_xmodal
+    std::vector<uint64_t> member;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (!clip_xmodal && !s->image_only.empty()) member = s->image_only;
+    }
+    if (!member.empty()) {
+        p.bitmap = member.data();
+        p.bitmap_stride_words = 0;
+    }
     if (use_quant) {
         // compute_query_quant with the pair's frozen scale happens on the GPU inside pkv_search
         // (f32 queries against an int8 index); the index must carry that same scale.
         pkv_index_info info;
         st = pkv_index_get_info(chosen.index, &info);
         if (st != PKV_OK) return st;
-        if (!info.has_scale || info.scale != chosen.pair.scale)
-            return fail(PKV_ERR_NOT_READY, "quant index scale does not match the ready pair's frozen scale");
-        st = pkv_search(chosen.index, queries, nq, &p, out_ids, out_dist, out_counts);
-        if (st == PKV_OK && used_profile_id) *used_profile_id = chosen.pair.profile_id;
-        return st;
+        const bool strict = index_mode == PKV_INDEX_QUANT || normalize_variant(variant_or_null, nullptr);
+        if (!info.has_scale || info.scale != chosen.pair.scale) {
+            // resolve_vector_quant never fails a non-strict `auto`: it falls back to exact (preprocess.rs:356-362)
+            if (strict) return fail(PKV_ERR_NOT_READY, "quant index scale does not match the ready pair's frozen scale");
+            use_quant = false;
+        } else {
+            if (!member.empty() && (int64_t)member.size() * 64 < info.rows)
+                return fail(PKV_ERR_INVALID, "the space's modality map covers fewer rows than its quant index");
+            st = pkv_search(chosen.index, queries, nq, &p, out_ids, out_dist, out_counts);
+            if (st == PKV_OK && used_profile_id) *used_profile_id = chosen.pair.profile_id;
+            return st;
+        }
     }
     if (!s->exact) return fail(PKV_ERR_NOT_READY, "space '%s' has no exact index", s->model.c_str());
     pkv_index_info info;

@@ -212,7 +212,9 @@ def test_similar_to_matches_reference_fixture_and_oracle():
     for code, data in ((pk.F32, seeded), (pk.I8, codes[:n])):
         with pk.VectorIndex(8, code) as ix:
             ix.append(data); ix.seal()
-            items, agg, cnt = pk.similar_to(ix, item, n, g["target_index"], pk.L2)
+            tgt = torch.tensor([g["target_index"]], dtype=torch.int64).cuda()
+            grp = torch.where(item == g["target_index"], torch.full_like(item, -1), item).contiguous()
+            items, agg, cnt = pk.similar_to(ix, tgt, grp, n, pk.L2)
             assert cnt == 7
             orders.append(list(items.cpu().numpy()[:cnt]))
     assert orders[0] == orders[1] and g["target_index"] not in orders[0]
@@ -223,7 +225,10 @@ def test_similar_to_matches_reference_fixture_and_oracle():
     with pk.VectorIndex(64, pk.F32) as ix:
         ix.append(x); ix.seal()
         for agg in (pk.AGG_AVG, pk.AGG_MIN):
-            items, vals, cnt = pk.similar_to(ix, torch.from_numpy(it).cuda(), 1000, 42, pk.COSINE, agg, limit=50)
+            itd = torch.from_numpy(it).cuda()
+            tgt = torch.nonzero(itd == 42).flatten().contiguous()
+            grp_d = torch.where(itd == 42, torch.full_like(itd, -1), itd).contiguous()
+            items, vals, cnt = pk.similar_to(ix, tgt, grp_d, 1000, pk.COSINE, agg, limit=50)
             tq = x[it == 42]
             dist = np.stack([orc.distances(x, t, orc.COSINE) for t in tq])
             grp = np.where(it == 42, -1, it)
@@ -279,3 +284,100 @@ def test_sqlite_table_valued_function_joins_like_the_distance_cte():
     for (f_got, agg_got, _), (f_want, agg_want) in zip(rows, ranked):
         assert abs(agg_got - agg_want) <= 1e-5 * max(abs(agg_want), abs(1 - agg_want)) + 1e-7
     assert [r[0] for r in raw] == data_ids[want[0][0][:7]].tolist() and [r[2] for r in raw] == list(range(1, 8))
+
+
+def _similar_reference(x, target_rows, grp, n_groups, metric, agg, modality=None, clip_xmodal=False, i2i=True, t2t=True,
+                       w=None):
+    """NumPy restatement of the self-join of item_similarity.rs:432-581 (float64 aggregates like SQLite)."""
+    acc = {}
+    for m in target_rows:
+        d = orc.distances(x, x[m], metric).astype(np.float64)
+        for r in range(len(x)):
+            g = grp[r]
+            if g < 0:
+                continue
+            if modality is not None:
+                rm, qm = modality[r], modality[m]
+                if not clip_xmodal and (rm != 0 or qm != 0):
+                    continue
+                if clip_xmodal and not i2i and rm == 0 and qm == 0:
+                    continue
+                if clip_xmodal and not t2t and rm == 1 and qm == 1:
+                    continue
+            ww = 1.0 if w is None else float(w[r]) * float(w[m])
+            acc.setdefault(g, []).append((d[r], ww))
+    out = {}
+    for g, pairs in acc.items():
+        ds = np.array([p[0] for p in pairs]); ws = np.array([p[1] for p in pairs])
+        if w is not None:
+            out[g] = float((ds * ws).sum() / ws.sum())
+        else:
+            out[g] = float({pk.AGG_MIN: ds.min(), pk.AGG_MAX: ds.max(), pk.AGG_AVG: ds.mean()}[agg])
+    return sorted(out.items(), key=lambda kv: (kv[1], kv[0]))
+
+
+@pytest.mark.parametrize("flags", [(False, True, True), (True, True, True), (True, False, True), (True, True, False),
+                                   (True, False, False)])
+def test_similar_to_cross_modal_pair_rules_and_weights(flags):
+    """a11/f2: clip_xmodal / xmodal_i2i / xmodal_t2t (item_similarity.rs:468-488) and the confidence weights
+    (:523-560) inside pkv_similar_to_device, one index holding the image setter's and the text sibling's rows."""
+    import torch
+
+    clip_xmodal, i2i, t2t = flags
+    rng = np.random.default_rng(91)
+    n, d, n_items = 900, 32, 300
+    x = orc.synthetic(n, d, 801)
+    item = rng.integers(0, n_items, size=n).astype(np.int64)
+    modality = (rng.random(n) < 0.4).astype(np.uint8)            # 40 % text-sibling rows
+    w = rng.uniform(0.2, 1.0, size=n).astype(np.float32)
+    target_item = int(item[5])
+    target_rows = np.nonzero(item == target_item)[0].astype(np.int64)
+    grp = np.where(item == target_item, -1, item)
+    with pk.VectorIndex(d, pk.F32) as ix:
+        ix.append(x)
+        ix.seal()
+        dev = lambda a: torch.from_numpy(a).cuda()
+        for agg, weights in ((pk.AGG_AVG, None), (pk.AGG_MIN, None), (pk.AGG_AVG, w)):
+            got_g, got_a, cnt = pk.similar_to(ix, dev(target_rows), dev(grp), n_items, pk.COSINE, agg,
+                                              weights=None if weights is None else dev(weights), modality=dev(modality),
+                                              clip_xmodal=clip_xmodal, xmodal_i2i=i2i, xmodal_t2t=t2t, limit=40)
+            want = _similar_reference(x, target_rows, grp, n_items, orc.COSINE, agg, modality, clip_xmodal, i2i, t2t, weights)
+            assert cnt == min(40, len(want))
+            got_vals = got_a.cpu().numpy()[:cnt]
+            assert np.allclose(got_vals, [v for _, v in want[:cnt]], rtol=2e-5, atol=1e-6)
+            assert len(set(got_g.cpu().numpy()[:cnt].tolist()) ^ {g for g, _ in want[:cnt]}) <= 2   # near-tie swaps
+        with pytest.raises(pk.PqlError, match="clip_xmodal needs the per-row modality"):
+            pk.similar_to(ix, dev(target_rows), dev(grp), n_items, pk.COSINE, clip_xmodal=True)
+
+
+def test_cross_modal_space_membership_and_auto_fallback():
+    """a6/a9: one space = image setter + "t"-sibling rows (db/vector_quants.rs:480-510); without clip_xmodal only
+    the image rows are members (image_embeddings.rs:140-199); a quant index whose scale disagrees with the ready pair
+    makes non-strict `auto` fall back to exact and strict `quant` fail (preprocess.rs:356-362)."""
+    rng = np.random.default_rng(92)
+    n, d = 30_000, 64
+    x, q, scale, xc, qc = int8_space(n, d, seed=811, nq=5)
+    modality = (rng.random(n) < 0.5).astype(np.uint8)
+    bm = np.packbits(np.concatenate([modality == 0, np.zeros((-n) % 64, bool)]), bitorder="little").view(np.uint64)
+    with pk.VectorIndex(d, pk.F32) as exact, pk.VectorIndex(d, pk.I8) as quant:
+        exact.append(x); exact.seal()
+        quant.set_scale_artifact(pk.scale_artifact(scale)); quant.append(xc); quant.seal()
+        sp = pk.Space("clip/ViT", exact)
+        sp.set_modality(modality)
+        sp.set_quant("int8-gsym", pk.ReadyPair(7, scale, d), quant)
+        ids, dist, cnt, used = sp.search(q, pk.COSINE, pk.INDEX_EXACT, depth=20)                  # image rows only
+        assert used == -1 and np.all(modality[ids] == 0)
+        assert_close_topk((ids, dist, cnt), orc.topk(x, q, orc.COSINE, 20, bitmap=bm, threads=4), x, q, orc.COSINE)
+        ids, dist, cnt, used = sp.search(q, pk.COSINE, pk.INDEX_EXACT, depth=20, clip_xmodal=True)  # the whole space
+        assert_close_topk((ids, dist, cnt), orc.topk(x, q, orc.COSINE, 20, threads=4), x, q, orc.COSINE)
+        assert np.any(modality[ids] == 1)
+        ids, dist, cnt, used = sp.search(q, pk.COSINE, pk.INDEX_AUTO, depth=20)                   # quant, image rows only
+        assert used == 7
+        assert_exact((ids, dist, cnt), orc.topk(xc, qc, orc.COSINE, 20, bitmap=bm, threads=4))
+        # the pair's frozen scale moved on (a rebuild is pending): auto falls back, quant refuses
+        sp.set_quant("int8-gsym", pk.ReadyPair(7, scale * 2, d), quant)
+        ids, dist, cnt, used = sp.search(q, pk.COSINE, pk.INDEX_AUTO, depth=20, clip_xmodal=True)
+        assert used == -1
+        with pytest.raises(pk.PqlError, match="frozen scale"):
+            sp.search(q, pk.COSINE, pk.INDEX_QUANT, depth=20)
+        sp.close()

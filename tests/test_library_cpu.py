@@ -142,3 +142,18 @@ def test_rank_fusion_matches_the_sql_expression():
     mx = {g: max(rank[i].get(g, -HUGE) for i in range(3)) for g in groups}
     got_g, got_s = pk.fuse_ranks(lists, "max")
     assert list(got_g) == sorted(groups, key=lambda g: (-mx[g], g))
+
+
+def test_cross_modal_host_policy():
+    """xmodal_text_sibling_name (db/vector_quants.rs:51-53) and the sibling rule of resolve_ready_pair (:1817-1867)."""
+    assert pk.xmodal_text_sibling_name("ViT-H-14-378-quickgelu/dfn5b") == "tViT-H-14-378-quickgelu/dfn5b"
+    s1 = float(np.float32(0.0125))                  # scales are f32 (the 4-byte artifact)
+    a = pk.ReadyPair(3, s1, 1024)
+    assert pk.resolve_ready_pair([a]) == a
+    assert pk.resolve_ready_pair([a, None]) == a                                   # the sibling setter does not exist: skipped
+    assert pk.resolve_ready_pair([a, pk.ReadyPair(3, s1, 1024)]) == a          # siblings share one artifact
+    assert pk.resolve_ready_pair([a, pk.ReadyPair(3, 0.02, 1024)]) is None         # scale differs: rebuild pending
+    assert pk.resolve_ready_pair([a, pk.ReadyPair(3, s1, 768)]) is None        # dim differs
+    assert pk.resolve_ready_pair([a, "not-ready"]) is None                        # an existing setter without a ready pair
+    assert pk.resolve_ready_pair([None, None]) is None and pk.resolve_ready_pair([]) is None
+    assert pk.resolve_ready_pair([pk.ReadyPair(3, float("nan"), 8)]) is None       # no usable scale
