@@ -390,6 +390,49 @@ int pkv_space_search(pkv_space *s, const float *queries, int nq, int query_dim, 
                      const char *variant_or_null, int64_t k_arg, int depth, int64_t *out_ids, float *out_dist,
                      int32_t *out_counts, int64_t *used_profile_id);
 
+/* -- corpus lifecycle: the HBM replica of one stored payload (db/vector_quants.rs:1085-1163 chunked backfill,
+ *    :1347-1438 inline hook, :1829-1850 readiness; db/epochs.rs:38-44 invalidation) ----------------------------------
+ * A pkv_corpus is the reference's pair state machine (pending -> building -> ready) around a pkv_index, keyed by
+ * (index_db, space, profile_id): filled by idempotent chunks at one artifact_rev, kept in sync by the inline hook,
+ * usable only while ready at the (artifact_rev, index epoch) the host reads from its DB.  f32 source blobs of an int8
+ * corpus are quantised on the GPU with the frozen scale (quantize_int8 of backfill_chunk / write_inline_quants). */
+typedef struct pkv_corpus pkv_corpus;
+typedef enum { PKV_CORPUS_PENDING = 0, PKV_CORPUS_BUILDING = 1, PKV_CORPUS_READY = 2 } pkv_corpus_state;
+typedef struct {
+    int32_t state; /* pkv_corpus_state */
+    int32_t dtype;
+    int32_t dim;
+    int32_t reserved;
+    int64_t profile_id;   /* -1: the exact f32 payload (`embeddings`) */
+    int64_t artifact_rev;
+    uint64_t index_epoch;
+    int64_t rows;
+    int64_t cursor;       /* largest item_data.id uploaded by chunks: the `d.id > ?` resume point of the backfill */
+} pkv_corpus_info;
+int pkv_corpus_create(int device, int dim, int dtype, const char *index_db, const char *space, int64_t profile_id,
+                      pkv_corpus **out);
+int pkv_corpus_destroy(pkv_corpus *c);
+const char *pkv_corpus_last_error(const pkv_corpus *c);
+/* -> building at (artifact_rev, epoch).  A new revision (or scale) drops the rows held; the same one resumes.  int8:
+ * the 4-byte scale artifact is mandatory and validated like artifact_scale. */
+int pkv_corpus_begin(pkv_corpus *c, int64_t artifact_rev, const uint8_t *artifact, size_t artifact_len, uint64_t index_epoch);
+/* One backfill chunk: n rows keyed by ascending item_data.id; rows at or below the cursor, or already added by the
+ * inline hook, are skipped (replaying a chunk writes nothing twice).  Zero rows are written when the pair is no
+ * longer building at this revision.  src_dtype: the corpus dtype, or PKV_F32 for an int8 corpus (GPU codec). */
+int pkv_corpus_upload_chunk(pkv_corpus *c, int64_t artifact_rev, const int64_t *ids, const void *blobs, int src_dtype,
+                            int64_t n, int64_t *written, int64_t *cursor);
+/* The inline hook: one freshly written embedding while building or ready (searchable at once when ready).  A blob of
+ * the wrong size downgrades the replica to pending and returns PKV_ERR_DIM_MISMATCH. */
+int pkv_corpus_append_inline(pkv_corpus *c, int64_t data_id, const void *blob, size_t blob_bytes, int src_dtype,
+                             uint64_t index_epoch);
+int pkv_corpus_finish(pkv_corpus *c, int64_t artifact_rev, uint64_t index_epoch);
+/* A write to the index DB that was not mirrored (bump_index_epoch): the replica is stale -> pending. */
+int pkv_corpus_invalidate(pkv_corpus *c);
+/* PKV_OK (+ the ReadyPair, + the searchable index, borrowed) only while ready at exactly this revision and epoch;
+ * PKV_ERR_NOT_READY otherwise - `auto` then falls back to exact, `quant` fails (pql/preprocess.rs:356-362). */
+int pkv_corpus_ready(pkv_corpus *c, int64_t artifact_rev, uint64_t index_epoch, pkv_ready_pair *pair, pkv_index **index);
+int pkv_corpus_get_info(pkv_corpus *c, pkv_corpus_info *info);
+
 /* -- cross-modal spaces (db/vector_quants.rs:480-510; image_embeddings.rs:140-199) -------------------------------------
  * A CLIP image setter and its "t"-prefixed text sibling form ONE space with one int8 scale; a filter without
  * clip_xmodal sees the image setter's rows only, with it both setters' rows.  One index holds the whole space. */

@@ -58,6 +58,14 @@ class RankParams(C.Structure):
     ]
 
 
+class CorpusInfo(C.Structure):
+    _fields_ = [
+        ("state", C.c_int32), ("dtype", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+        ("profile_id", C.c_int64), ("artifact_rev", C.c_int64), ("index_epoch", C.c_uint64), ("rows", C.c_int64),
+        ("cursor", C.c_int64),
+    ]
+
+
 class SimilarParams(C.Structure):
     _fields_ = [
         ("metric", C.c_int32), ("aggregation", C.c_int32), ("offset", C.c_int32), ("limit", C.c_int32),
@@ -124,6 +132,17 @@ SIGNATURES = {
     "pkv_space_set_modality": (C.c_int, [_P, _P, C.c_int64]),
     "pkv_space_search_xmodal": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64, C.c_int,
                                           C.c_int, _P, _P, _P, C.POINTER(C.c_int64)]),
+    "pkv_corpus_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(_P)]),
+    "pkv_corpus_destroy": (C.c_int, [_P]),
+    "pkv_corpus_last_error": (C.c_char_p, [_P]),
+    "pkv_corpus_begin": (C.c_int, [_P, C.c_int64, _P, C.c_size_t, C.c_uint64]),
+    "pkv_corpus_upload_chunk": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, C.c_int64, C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64)]),
+    "pkv_corpus_append_inline": (C.c_int, [_P, C.c_int64, _P, C.c_size_t, C.c_int, C.c_uint64]),
+    "pkv_corpus_finish": (C.c_int, [_P, C.c_int64, C.c_uint64]),
+    "pkv_corpus_invalidate": (C.c_int, [_P]),
+    "pkv_corpus_ready": (C.c_int, [_P, C.c_int64, C.c_uint64, _P, C.POINTER(_P)]),
+    "pkv_corpus_get_info": (C.c_int, [_P, _P]),
     "pkv_sqlite_register_index": (C.c_int, [C.c_char_p, _P]),
     "pkv_aggregate_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "pkv_index_counters": (C.c_int, [_P, C.POINTER(Counters)]),

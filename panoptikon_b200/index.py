@@ -337,6 +337,77 @@ class Comm:
         return out
 
 
+class Corpus:
+    """Lifecycle of the HBM replica of one stored payload (pkv_corpus_*): pending -> building -> ready, filled by
+    idempotent chunks at one artifact_rev, kept in sync by the inline hook, usable only at the (rev, epoch) asked for."""
+    PENDING, BUILDING, READY = 0, 1, 2
+
+    def __init__(self, dim: int, dtype: int, index_db: str, space: str, profile_id: int = -1, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().pkv_corpus_create(device, dim, dtype, index_db.encode(), space.encode(), profile_id,
+                                          C.byref(self._h)))
+        self.dim, self.dtype = dim, dtype
+
+    def close(self) -> None:
+        if self._h:
+            N.lib().pkv_corpus_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st: int) -> None:
+        if st != N.OK:
+            msg = N.lib().pkv_corpus_last_error(self._h).decode("utf-8", "replace") or N.last_error()
+            raise N.PkvError(st, msg)
+
+    def begin(self, artifact_rev: int, artifact: Optional[bytes], index_epoch: int) -> None:
+        a = artifact or b""
+        buf = (C.c_uint8 * max(len(a), 1)).from_buffer_copy(a.ljust(1, b"\0"))
+        self._check(N.lib().pkv_corpus_begin(self._h, artifact_rev, buf, len(a), index_epoch))
+
+    def upload_chunk(self, artifact_rev: int, ids, blobs: np.ndarray):
+        """-> (rows written, cursor)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        blobs = np.ascontiguousarray(blobs)
+        written, cursor = C.c_int64(), C.c_int64()
+        self._check(N.lib().pkv_corpus_upload_chunk(self._h, artifact_rev, _np_ptr(ids), _np_ptr(blobs),
+                                                    _CODE[blobs.dtype], len(ids), C.byref(written), C.byref(cursor)))
+        return int(written.value), int(cursor.value)
+
+    def append_inline(self, data_id: int, blob: np.ndarray, index_epoch: int) -> None:
+        blob = np.ascontiguousarray(blob)
+        self._check(N.lib().pkv_corpus_append_inline(self._h, data_id, _np_ptr(blob), blob.nbytes, _CODE[blob.dtype],
+                                                     index_epoch))
+
+    def finish(self, artifact_rev: int, index_epoch: int) -> None:
+        self._check(N.lib().pkv_corpus_finish(self._h, artifact_rev, index_epoch))
+
+    def invalidate(self) -> None:
+        self._check(N.lib().pkv_corpus_invalidate(self._h))
+
+    def info(self) -> N.CorpusInfo:
+        out = N.CorpusInfo()
+        self._check(N.lib().pkv_corpus_get_info(self._h, C.byref(out)))
+        return out
+
+    def ready(self, artifact_rev: int, index_epoch: int):
+        """The searchable VectorIndex view (borrowed) and the ReadyPair, or None when not ready at (rev, epoch)."""
+        pair = N.ReadyPair()
+        h = C.c_void_p()
+        st = N.lib().pkv_corpus_ready(self._h, artifact_rev, index_epoch, C.byref(pair), C.byref(h))
+        if st == N.ERR_NOT_READY:
+            return None
+        self._check(st)
+        view = VectorIndex.__new__(VectorIndex)
+        view._h, view.dim, view.dtype, view.device = h, self.dim, self.dtype, 0
+        view.close = lambda: None          # borrowed: the corpus owns the index
+        return view, (int(pair.profile_id), float(pair.scale), int(pair.dim))
+
+
 # ---- codec (db/vector_quants.rs:1446-1503) -------------------------------------
 
 def scale_from_absmax(absmax: float) -> float:
