@@ -289,9 +289,11 @@ int pkv_comm_unique_id(uint8_t *out, size_t len /* 128 */);
 int pkv_comm_create(int device, int rank, int nranks, const uint8_t *unique_id, size_t len /* 128 */, pkv_comm **out);
 int pkv_comm_destroy(pkv_comm *h);
 int pkv_comm_info(const pkv_comm *h, int *rank, int *nranks);
-/* Every rank calls this with ITS shard and the SAME queries (device buffers); on return every rank holds the global
+/* Every rank calls this with ITS shard and the SAME queries (device buffers); every rank ends up with the global
  * top-k.  The exchange is ONE ncclAllGather of the packed per-shard lists (nq*k*12 bytes per rank) enqueued behind the
- * scan on `stream`, then the merge kernel reading the gathered buffer.  Collective: all ranks, same order. */
+ * scan on `stream`, then the merge kernel reading the gathered buffer.  The shard's scan has completed on return; the
+ * exchange is only enqueued: the outputs are complete once `stream` is synchronised.  Collective: all ranks, same
+ * order; one call at a time per communicator and stream. */
 int pkv_search_sharded_device(pkv_index *shard, pkv_comm *comm, const void *d_queries, int nq,
                               const pkv_search_params *params, int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_counts,
                               void *stream);
@@ -335,12 +337,13 @@ typedef struct {
     int64_t deferred_pairs;     /* ... parked by a live launch and re-scored behind it, after the final-threshold check */
 } pkv_counters;
 int pkv_index_counters(pkv_index *h, pkv_counters *out);
-/* Tuning knobs for tests and the bench: "image_mask" (which filter images an f32/f16
- * index builds at seal: bit 1 int8, bit 0 fp16; set before the first append), "use_shadow" (-1 best available,
- * 2 int8 image, 1 fp16 image, 0 none), "img8_max_queries", "img8_peak_sigma_x10", "force_simt", "tc_ts",
- * "ts_groups", "ts_chunks", "ts_stages", "ts_acc_buffers", "tc_cta2", "tc_min_queries", "tc_min_queries_f32",
- * "tc_min_queries_img", "candidate_capacity", "first_chunk_rows", "chunk_growth_x100", "optimistic",
- * "simt_bootstrap", "combine", "time_kernels", "tc_prefetch_tiles".  Unknown names are PKV_ERR_INVALID. */
+/* Options of an index.  Production: "image_mask" (which filter images an f32/f16 index builds at seal: bit 1 int8,
+ * bit 0 fp16; set before the first append), "use_shadow" (which image searches scan: -1 best available, 2 int8, 1 fp16,
+ * 0 none), "combine" (merge concurrent small host searches into one scan), "live" (0 never / 1 auto / 2 always: one
+ * launch over the bulk of a large corpus with thresholds maintained in-kernel), "time_kernels".  Everything else the
+ * call accepts is a test / experiment switch that forces a particular kernel or schedule so that the parity tests can
+ * compare them; those are listed in INTEGRATION.md section 4 and are not part of the supported surface.  Unknown names
+ * are PKV_ERR_INVALID. */
 int pkv_index_set_option(pkv_index *h, const char *name, int64_t value);
 
 /* -- PQL operator policy: pql/preprocess.rs:314-465, builder/filters/embedding_types.rs --- */

@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const ScanArgs a, const Pe
         atomicOr(&status->sticky_overflow, 1u);
     }
     if (n == 0) return;
+    if (blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&status->rescored, n);  // search statistics (pkv_counters)
     const float4 *gq = (const float4 *)a.queries + (size_t)q * nvec;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) s_q[i] = gq[i];
     __syncthreads();

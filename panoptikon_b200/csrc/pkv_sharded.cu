@@ -399,7 +399,8 @@ int pkv_search_sharded_device(pkv_index *shard, pkv_comm *comm, const void *d_qu
     PKV_TRY(launch_pack_topk(l_ids, l_dist, (int64_t)entries, c->d_packed, s));
     PKV_NCCL(n.AllGather(c->d_packed, c->d_gathered, entries * 12, NCCL_UINT8, c->comm, s));
     PKV_TRY(launch_merge_packed(c->d_gathered, c->nranks, nq, params->k, d_out_ids, d_out_dist, d_out_counts, s));
-    PKV_CUDA(cudaStreamSynchronize(s));
+    // the exchange is only ENQUEUED: the outputs are complete once `stream` has been synchronised (the next search on
+    // the same stream orders behind it by itself)
     return PKV_OK;
 }
 

@@ -318,7 +318,8 @@ class Comm:
             self._h = C.c_void_p()
 
     def search(self, index: "VectorIndex", queries, k: int, metric: int = N.COSINE, bitmap=None, out=None):
-        """Every rank: its shard + the same torch CUDA queries -> the global top-k (CUDA tensors) on every rank."""
+        """Every rank: its shard + the same torch CUDA queries -> the global top-k (CUDA tensors) on every rank.
+        The exchange is enqueued on the current stream (torch orders later work on that stream behind it)."""
         import torch
 
         assert queries.is_cuda and queries.is_contiguous() and queries.dim() == 2
