@@ -86,6 +86,7 @@ Workspace::~Workspace() {
     cudaFree(d_defer_rows);
     cudaFree(d_defer_dots);
     cudaFree(d_defer_cnt);
+    cudaFree(d_defer_meta);
     cudaFree(d_q16);
     cudaFree(d_q8);
     cudaFree(d_q8_meta);
@@ -164,6 +165,7 @@ static int make_workspace(Index &ix, int nq, int k, size_t out_rows, Workspace *
             A((void **)&ws->d_defer_rows, sizeof(uint32_t) * (size_t)nq_cap * ws->pend_cap);
             A((void **)&ws->d_defer_dots, sizeof(int) * (size_t)nq_cap * ws->pend_cap);
             A((void **)&ws->d_defer_cnt, sizeof(uint32_t) * nq_cap);
+            A((void **)&ws->d_defer_meta, sizeof(float4) * (size_t)nq_cap * ws->pend_cap);
             A((void **)&ws->d_q16, sizeof(__half) * (size_t)nq_cap * ix.dim_pad_h);
             A((void **)&ws->d_q_scale, sizeof(float) * nq_cap);
             A((void **)&ws->d_q8, (size_t)nq_cap * ix.dim_pad8);
@@ -345,8 +347,8 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // that the in-kernel feedback (re-score -> re-select -> re-read, ~10 us = tens of thousands of rows scanned
     // meanwhile) cannot keep up; behind ~64k rows the pass rate is low enough for the lag not to matter.
     const int64_t live_start = ix.opt.live_start_rows > 0 ? ix.opt.live_start_rows : 131072;
-    // Measured on B200 (profiles/README.md, round 2): the live launch has a start-up transient and a drain tail of
-    // ~0.4 ms that only a long scan amortises; below ~4M rows the chunked schedule with deferred band pairs is faster.
+    // Measured on B200 (profiles/README.md, round 2): the live launch has a start-up transient and a drain tail that
+    // only a long enough scan amortises; below ~0.7M rows the chunked schedule with deferred band pairs is faster.
     if (ix.opt.live == 1 && N - live_start < ix.opt.live_min_rows) r.live_capable = false;
     ScanArgs &a = r.args;
     a.data = ix.d_data;

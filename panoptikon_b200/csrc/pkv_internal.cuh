@@ -189,6 +189,7 @@ struct Workspace {
     uint32_t *d_defer_rows = nullptr;
     int *d_defer_dots = nullptr;
     uint32_t *d_defer_cnt = nullptr;
+    float4 *d_defer_meta = nullptr;
     __half *d_q16 = nullptr;          // fp16-image path: scaled half queries [nq_cap][dim_pad_h]
     int8_t *d_q8 = nullptr;           // int8-image path: per-query quantised codes [nq_cap][dim_pad8]
     float4 *d_q8_meta = nullptr;      // {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2} per query
@@ -239,7 +240,7 @@ struct Options {
     int img8_fused = 1;              // int8-image path, exact re-scoring by warps of the scan kernel itself: 0 never
                                      // (no live launches either), 1 in live launches, 2 in every launch
     int64_t live_start_rows = 0;     // rows scanned on the chunked schedule before the live launch (0 = auto)
-    int64_t live_min_rows = 4000000; // live = 1: only when the live launch would cover at least this many rows (2 = always)
+    int64_t live_min_rows = 600000;  // live = 1: only when the live launch would cover at least this many rows (2 = always)
 };
 
 // Concurrent small searches (the server issues one query per request thread, 16 pool threads:
@@ -306,6 +307,8 @@ struct PendDev {
     uint32_t cap;
     int *dots;       // [nq][cap] the filter's integer dot product (int8-image path: deferred pairs are re-checked
                      // against the final threshold before their rows are gathered); may be NULL elsewhere
+    float4 *meta;    // [nq][cap] the row figures of the parked pair (the re-check then reads its list sequentially
+                     // instead of gathering row_meta at random); may be NULL elsewhere
 };
 
 // ---- kernels / launchers (each returns a pkv_status) ----

@@ -208,6 +208,7 @@ __device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, 
     if (slot < im.dlist.cap) {
         im.dlist.rows[(size_t)q * im.dlist.cap + slot] = row;
         im.dlist.dots[(size_t)q * im.dlist.cap + slot] = d;
+        im.dlist.meta[(size_t)q * im.dlist.cap + slot] = m;
     }
 }
 
@@ -430,6 +431,7 @@ __device__ __forceinline__ void rescore_loop(const ScanArgs &a, const ImgArgs &i
                 if (slot < im.dlist.cap) {
                     im.dlist.rows[(size_t)q * im.dlist.cap + slot] = row;
                     im.dlist.dots[(size_t)q * im.dlist.cap + slot] = d;
+                    im.dlist.meta[(size_t)q * im.dlist.cap + slot] = __ldg(im.row_meta + row);
                 }
             }
             continue;
@@ -824,7 +826,7 @@ __global__ void __launch_bounds__(256) rescore_deferred_kernel(const ScanArgs a,
         if (e < n) {
             row = im.dlist.rows[(size_t)q * im.dlist.cap + e];
             const int d = im.dlist.dots[(size_t)q * im.dlist.cap + e];
-            const float4 m = __ldg(im.row_meta + row);
+            const float4 m = im.dlist.meta[(size_t)q * im.dlist.cap + e];
             float x1, x2;
             row_figures<METRIC>(m, x1, x2);
             keep = !((float)d < pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x));
@@ -1137,8 +1139,8 @@ static ImgArgs img_args(const Index &ix, const ScanArgs &a, Workspace &ws) {
     im.row_meta = ix.d_img8_meta;
     im.q8 = ws.d_q8;
     im.q_meta = ws.d_q8_meta;
-    im.pend = PendDev{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap, nullptr};
-    im.dlist = PendDev{ws.d_defer_rows, ws.d_defer_cnt, (uint32_t)ws.pend_cap, ws.d_defer_dots};
+    im.pend = PendDev{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap, nullptr, nullptr};
+    im.dlist = PendDev{ws.d_defer_rows, ws.d_defer_cnt, (uint32_t)ws.pend_cap, ws.d_defer_dots, ws.d_defer_meta};
     im.dim_pad8 = ix.dim_pad8;
     // live launches always re-score in-kernel: the thresholds can only move while the scan runs if the exact
     // scores are produced while it runs.  The chunks before it keep the separate re-score kernel (every SM gathers
@@ -1154,7 +1156,7 @@ int launch_rescore_deferred(const Index &ix, const ScanArgs &a, Workspace &ws, c
     if (a.nq <= 0) return PKV_OK;
     const ImgArgs im = img_args(ix, a, ws);
     const size_t smem = (size_t)a.dim_pad * 4;
-    int ry = (4 * ix.sm_count + a.nq - 1) / a.nq;  // ~4 CTAs per SM in total
+    int ry = (8 * ix.sm_count + a.nq - 1) / a.nq;  // ~8 CTAs (64 warps) per SM in total: the gathers are latency-bound
     if (ry < 1) ry = 1;
     if (ry > 64) ry = 64;
     const dim3 grid((unsigned)a.nq, (unsigned)ry);

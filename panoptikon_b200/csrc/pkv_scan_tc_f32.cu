@@ -651,7 +651,7 @@ __global__ void shadow_convert_kernel(const float *rows, int64_t pitch_f, int di
 // Exact re-scoring of everything the filter kernels parked in `pend` (one launch for all queries).
 int launch_rescore(const Index &ix, const ScanArgs &a, const PendDev &pend, SearchStatus *status, cudaStream_t s) {
     const size_t smem = (size_t)a.dim_pad * 4;
-    int ry = (4 * ix.sm_count + a.nq - 1) / a.nq;  // ~4 CTAs per SM in total
+    int ry = (8 * ix.sm_count + a.nq - 1) / a.nq;  // ~8 CTAs (64 warps) per SM in total: the gathers are latency-bound
     if (ry < 1) ry = 1;
     if (ry > 64) ry = 64;
     const dim3 grid((unsigned)a.nq, (unsigned)ry);
@@ -742,7 +742,7 @@ int build_shadow(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s) 
 int launch_scan_tc_f32(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
     if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
     if (image_choice(ix, a.nq) == 2) return launch_scan_img8(ix, a, ws, s, launches);
-    PendDev pend{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap, nullptr};
+    PendDev pend{ws.d_pend_rows, ws.d_pend_cnt, (uint32_t)ws.pend_cap, nullptr, nullptr};
     PKV_CUDA(cudaMemsetAsync(ws.d_pend_cnt, 0, sizeof(uint32_t) * a.nq, s));
     FloatScan fsn;
     fsn.eps = float_eps(ix, a.nq);
