@@ -405,6 +405,20 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     static const bool trace_env = getenv("PKV_TRACE") != nullptr;
     bool optimistic = ix.opt.optimistic && !d_bitmap && !trace_env;
     bool allow_live = r.live_capable;
+    // Guessed start (mid-size corpora): instead of LEARNING the thresholds chunk by chunk, guess them - the
+    // guess_rank-th best of a strided sample of the corpus, a real row's distance that about guess_factor * k rows
+    // of the corpus beat - start the candidate lists empty, run ONE live launch over every row, and verify at the end:
+    // a query that found k rows under its guess has provably missed nothing; otherwise the search is redone on the
+    // learning schedule.  The sample holds >= 4 rows better than the guess, so a miss needs the corpus' best rows to be
+    // ~40x rarer than the sample says (adversarial insertion orders are what the strided sample defends against).
+    int guess_rank = 0;
+    if (allow_live && ix.opt.guess && optimistic && ix.sample_rows > 0 && ix.sample_of_rows == N &&
+        N <= ix.opt.guess_max_rows && ix.sample_rows <= r.safe_rows && ix.opt.live_start_rows == 0) {
+        const double want = (double)ix.opt.guess_factor * (double)k * (double)ix.sample_rows / (double)N;
+        guess_rank = (int)(want + 0.5);
+        if (guess_rank > k) guess_rank = k;
+        if (guess_rank < 4) guess_rank = 0;
+    }
 restart:
     int64_t pos = 0;
     r.min_filled = 0;
@@ -413,6 +427,22 @@ restart:
     r.outputs_written = false;
     r.defer_dirty = false;
     int64_t prev_chunk = 0;
+    if (guess_rank > 0) {
+        ScanArgs sa = r.args;
+        sa.data = ix.d_sample;
+        sa.row_mag_i = ix.d_sample_mag_i;
+        sa.row_begin = 0;
+        sa.row_end = (uint32_t)ix.sample_rows;
+        sa.topk.live = 0;
+        int n = 0;
+        PKV_TRY(launch_scan_simt(ix, sa, s, &n));  // every (query, sample row) pair, exactly
+        PKV_TRY(launch_select(ix, ws, nq, k, r.fs, /*clear_tail=*/true, false, nullptr, nullptr, nullptr, s, guess_rank));
+        r.launches += n + 1;
+        r.scan_launches += n;
+        r.min_filled = (uint32_t)k;  // every query has a threshold now
+        PKV_TRY(scan_range(r, 0, N, /*sync=*/false, /*live=*/true, /*last=*/true));
+        pos = N;
+    }
     while (pos < N) {
         const bool filled = r.min_filled >= (uint32_t)k;
         const bool go_live = allow_live && filled && pos >= live_start;
@@ -464,7 +494,17 @@ restart:
                 r.scan_ms += ms;
             }
         }
+        if (guess_rank > 0 && !ws.h_status->sticky_overflow && !ws.h_status->defer_overflow &&
+            ws.h_status->min_filled < (uint32_t)(N < k ? N : k)) {
+            // some query found fewer than k rows under its guessed threshold: the guess was too tight for it.
+            // Redo the search with learnt thresholds (still optimistic, still live).
+            r.depth_overflows++;
+            guess_rank = 0;
+            PKV_TRY(launch_reset_state(ws, nq, s));
+            goto restart;
+        }
         if (ws.h_status->sticky_overflow) {
+            guess_rank = 0;
             // a candidate buffer overflowed somewhere along the unsynced chunks: redo the search on the careful
             // schedule (a sync per chunk, overflowing ranges split, thresholds fixed per launch, nothing deferred)
             r.depth_overflows++;
@@ -477,6 +517,7 @@ restart:
         }
     }
     if (r.defer && ws.h_status->defer_overflow) {
+        guess_rank = 0;
         // a query parked more pairs than its list holds (status as of the last sync, which followed the deferred pass)
         r.depth_overflows++;
         optimistic = false;
@@ -949,6 +990,8 @@ int pkv_index_destroy(pkv_index *h) {
     cudaFree(ix->d_shadow);
     cudaFree(ix->d_img8);
     cudaFree(ix->d_img8_meta);
+    cudaFree(ix->d_sample);
+    cudaFree(ix->d_sample_mag_i);
     delete ix;
     return PKV_OK;
 }
@@ -1026,6 +1069,7 @@ int pkv_index_seal(pkv_index *h) {
             PKV_TRY(build_shadow(ix, from, ix.rows, nullptr));
         }
         if (ix.d_img8) PKV_TRY(build_img8(ix, ix.image_rows < ix.sealed_rows ? ix.image_rows : ix.sealed_rows, ix.rows, nullptr));
+        PKV_TRY(build_sample(ix, nullptr));
         PKV_CUDA(cudaDeviceSynchronize());
         ix.sealed_rows = ix.rows;
         ix.image_rows = ix.rows;
@@ -1301,6 +1345,9 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "img8_defer")) ix.opt.img8_defer = (int)value;
     else if (!strcmp(name, "live_start_rows")) ix.opt.live_start_rows = value;
     else if (!strcmp(name, "live_min_rows")) ix.opt.live_min_rows = value;
+    else if (!strcmp(name, "guess")) ix.opt.guess = (int)value;
+    else if (!strcmp(name, "guess_max_rows")) ix.opt.guess_max_rows = value;
+    else if (!strcmp(name, "guess_factor")) ix.opt.guess_factor = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;
 }

@@ -240,6 +240,11 @@ struct Options {
     int img8_fused = 1;              // int8-image path, exact re-scoring by warps of the scan kernel itself: 0 never
                                      // (no live launches either), 1 in live launches, 2 in every launch
     int64_t live_start_rows = 0;     // rows scanned on the chunked schedule before the live launch (0 = auto)
+    int guess = 1;                   // start the live launch from thresholds GUESSED on a strided sample (verified at the
+                                     // end: a query that did not find k rows under its guess redoes the search)
+    int64_t guess_max_rows = 1600000; // ... for corpora up to this many rows (the sample must hold a few rows better
+                                     // than the guess: beyond, the chunked prefix learns the thresholds)
+    int guess_factor = 16;           // the guess aims at this many times k rows beating it
     int64_t live_min_rows = 600000;  // live = 1: only when the live launch would cover at least this many rows (2 = always)
 };
 
@@ -285,6 +290,12 @@ struct Index {
     int dim_pad8 = 0;           // bytes per int8 image row (multiple of 128)
     int64_t image_rows = 0;     // rows whose images are built
     float img8_U = 0.f;         // code length |a|/s_a of every int8-image row (0 = not fixed yet)
+    // threshold-guess sample: SAMPLE_ROWS stored rows taken at a constant stride over the sealed corpus (a copy, in
+    // the index dtype and pitch) + their int8 norms; searched densely to GUESS each query's starting threshold
+    uint8_t *d_sample = nullptr;
+    int32_t *d_sample_mag_i = nullptr;
+    int64_t sample_rows = 0;    // rows in the block (0 = not built)
+    int64_t sample_of_rows = 0; // sealed_rows the block was drawn from
     float shadow_absmax = 0.f;
     bool has_scale = false;
     float scale = 1.0f;
@@ -348,7 +359,8 @@ int launch_reset_status(Workspace &ws, cudaStream_t s);
 int launch_prep_queries(const Index &ix, Workspace &ws, const void *d_qraw, int nq, int query_dtype, cudaStream_t s);
 int launch_reset_state(Workspace &ws, int nq, cudaStream_t s);
 int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, bool clear_deferred,
-                  int64_t *d_ids, float *d_dist, int32_t *d_counts, cudaStream_t s);
+                  int64_t *d_ids, float *d_dist, int32_t *d_counts, cudaStream_t s, int guess_rank = 0);
+int build_sample(Index &ix, cudaStream_t s);
 int launch_finalize(const Index &ix, Workspace &ws, int nq, int k, int64_t *d_ids, float *d_dist, int32_t *d_counts,
                     cudaStream_t s);
 int launch_row_mags(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t s);

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *c
                                                      const float *q_mag_f, SearchStatus *status, uint32_t cap, int k,
                                                      FilterSpec fs, uint32_t *pend_cnt, uint32_t *defer_cnt, int clear_tail,
                                                      const int64_t *row_ids, int64_t row_base, int64_t *out_ids,
-                                                     float *out_dist, int32_t *out_counts) {
+                                                     float *out_dist, int32_t *out_counts, int guess_rank) {
     extern __shared__ uint64_t s_keys[];
     __shared__ uint64_t s_kth;
     __shared__ int s_m;
@@ -159,6 +159,13 @@ __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *c
             uint32_t m = out < (uint32_t)k ? out : (uint32_t)k;
             s_m = (int)m;
             s_kth = m == (uint32_t)k ? kth : KEY_MAX;
+            // guess mode: the keys are those of a SAMPLE of the corpus; the threshold the scan starts from is the
+            // guess_rank-th best of the sample (a real row's distance: about guess_rank * N / sample rows beat it) and
+            // the candidate list starts empty - the sample's rows are found again by the scan itself
+            if (guess_rank > 0) {
+                s_kth = (uint32_t)guess_rank <= n ? s_keys[guess_rank - 1] | 0xFFFFFFFFull : KEY_MAX;
+                s_m = 0;
+            }
         }
     }
     __syncthreads();
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(512) select_kernel(uint64_t *cand, uint32_t *c
             atomicOr(&status->any_overflow, 1u);
             atomicOr(&status->sticky_overflow, 1u);
         }
-        atomicMin(&status->min_filled, m);
+        if (guess_rank <= 0) atomicMin(&status->min_filled, m);  // (a guess select starts the list empty on purpose)
     }
     const uint32_t m_all = (uint32_t)s_m;
     if (clear_tail)
@@ -482,14 +489,14 @@ int launch_reset_status(Workspace &ws, cudaStream_t s) {
 }
 
 int launch_select(const Index &ix, Workspace &ws, int nq, int k, FilterSpec fs, bool clear_tail, bool clear_deferred,
-                  int64_t *d_ids, float *d_dist, int32_t *d_counts, cudaStream_t s) {
+                  int64_t *d_ids, float *d_dist, int32_t *d_counts, cudaStream_t s, int guess_rank) {
     if (nq <= 0) return PKV_OK;
     const size_t smem = (size_t)ws.cap * sizeof(uint64_t);
     PKV_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_kernel<<<nq, 512, smem, s>>>(ws.d_cand, ws.d_cnt, ws.d_thr_key, ws.d_thr_f, ws.d_q_mag_f, ws.d_status,
                                         (uint32_t)ws.cap, k, fs, ws.d_pend_cnt, clear_deferred ? ws.d_defer_cnt : nullptr,
                                         clear_tail ? 1 : 0, ix.d_ids,
-                                        ix.row_base, d_ids, d_dist, d_counts);
+                                        ix.row_base, d_ids, d_dist, d_counts, guess_rank);
     PKV_CUDA(cudaGetLastError());
     return PKV_OK;
 }
@@ -510,6 +517,40 @@ int launch_row_mags(Index &ix, int64_t row_begin, int64_t row_end, cudaStream_t 
     row_mags_kernel<<<(unsigned)blocks, warps * 32, 0, s>>>(ix.d_data, ix.pitch, ix.dim_pad, ix.dtype, row_begin,
                                                             row_end, ix.d_mag_i, ix.d_mag_f);
     PKV_CUDA(cudaGetLastError());
+    return PKV_OK;
+}
+
+// ---- threshold-guess sample: rows 0, stride, 2 stride, ... of the sealed corpus, copied into one contiguous block
+__global__ void sample_copy_kernel(const uint8_t *data, int64_t pitch, int64_t stride, int64_t n, uint8_t *out) {
+    const int64_t r = blockIdx.x;
+    if (r >= n) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(data + (size_t)(r * stride) * (size_t)pitch);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)r * (size_t)pitch);
+    for (int i = threadIdx.x; i < (int)(pitch / 16); i += blockDim.x) dst[i] = src[i];
+}
+
+constexpr int64_t SAMPLE_ROWS = 3968;  // <= candidate capacity - k for every k the guessed start serves (k <= 128)
+
+int build_sample(Index &ix, cudaStream_t s) {
+    const int64_t N = ix.rows;
+    if (N < 16 * SAMPLE_ROWS) {  // small corpora use the plain schedule
+        ix.sample_rows = 0;
+        return PKV_OK;
+    }
+    if (!ix.d_sample) {
+        PKV_CUDA(cudaMalloc((void **)&ix.d_sample, (size_t)SAMPLE_ROWS * ix.pitch));
+        if (ix.dtype == PKV_I8) PKV_CUDA(cudaMalloc((void **)&ix.d_sample_mag_i, sizeof(int32_t) * SAMPLE_ROWS));
+    }
+    const int64_t stride = N / SAMPLE_ROWS;
+    sample_copy_kernel<<<(unsigned)SAMPLE_ROWS, 128, 0, s>>>(ix.d_data, ix.pitch, stride, SAMPLE_ROWS, ix.d_sample);
+    if (ix.dtype == PKV_I8) {
+        const int warps = 8;
+        row_mags_kernel<<<(unsigned)((SAMPLE_ROWS + warps - 1) / warps), warps * 32, 0, s>>>(
+            ix.d_sample, ix.pitch, ix.dim_pad, ix.dtype, 0, SAMPLE_ROWS, ix.d_sample_mag_i, nullptr);
+    }
+    PKV_CUDA(cudaGetLastError());
+    ix.sample_rows = SAMPLE_ROWS;
+    ix.sample_of_rows = N;
     return PKV_OK;
 }
 

@@ -19,7 +19,8 @@ def _line(name):
     raise AssertionError(f"no JSON line in {name}")
 
 
-@pytest.mark.parametrize("name", ["r01_final_f32_b256.json", "r01_final_i8_b1024.json"])
+@pytest.mark.parametrize("name", ["r01_final_f32_b256.json", "r01_final_i8_b1024.json", "r02_final_default.json",
+                                  "r02_final_i8_b1024.json"])
 def test_our_arm_line_has_the_contract_keys(name):
     j = _line(name)
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -57,3 +58,23 @@ def test_multi_gpu_lines_scale():
     for n in (2, 4, 8):
         j = _line(f"r01_final_multi_f32_b256_n{n}.json")
         assert j["n_gpus"] == n and j["scaling"] == "strong" and j["value"] > one
+
+
+def test_round2_default_line_carries_the_targets_and_the_measured_peak():
+    """C2 / C3 sub-records, the int8 tensor peak measured in the same run, counted traffic,
+    a sustained figure, and a parity leg that names the batch shape that was timed."""
+    j = _line("r02_final_default.json")
+    r = j["roofline"]
+    assert r["bound"] == "tensor" and r["int8_peak_measured"]["int8_tops_burst"] > 1000
+    assert abs(r["peak"] - r["int8_peak_measured"]["int8_tops_burst"]) < 1e-6 and "measured in this run" in r["peak_source"]
+    assert "f32_hbm_roofline_frac" not in r and "counted" in r["traffic_note"]
+    assert r["traffic"] > r["algorithmic_bytes_per_step"]          # the re-scorer's reads are in
+    s = j["sustained"]
+    assert s["seconds"] >= 3.0 and s["value"] > 0 and s["clocks"]["sm_mhz"] > 0
+    assert "all 256 queries of the timed batch shape" in j["parity"]["checked"]
+    c2, c3 = j["configs"]["C2"], j["configs"]["C3"]
+    assert c2["workload"].startswith("1Mx768 f32 cosine") and "batch=256" in c2["workload"] and c2["value"] > 0
+    assert c3["workload"].startswith("10Mx768 i8 dot") and "batch=1024" in c3["workload"]
+    assert c3["roofline"]["tensor_frac_of_nominal"] >= 0.40          # north_star: >= 40 % of the int8 tensor-pipe peak
+    ref = _line("r02_final_reference.json")
+    assert ref["config"] == j["config"], "both arms must describe the same configuration"

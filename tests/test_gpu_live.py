@@ -118,6 +118,8 @@ def test_live_adversarial_order_falls_back():
     order = np.argsort(x @ q[0])   # ascending similarity = descending cosine distance
     x = np.ascontiguousarray(x[order])
     with _f32_index(x) as ix:
+        ix.set_option("guess", 0)          # learnt thresholds: the prefix sees only the worst rows
+        ix.set_option("live_start_rows", 4096)
         got = ix.search(q, 50, pk.COSINE)
         assert ix.counters().fallback_queries > 0
     assert_close_topk(got, orc.topk(x, q, orc.COSINE, 50, threads=5), x, q, orc.COSINE)
@@ -177,3 +179,51 @@ def test_device_api_orders_behind_the_callers_stream():
         got = (ids.cpu().numpy(), dist.cpu().numpy(), cnt.cpu().numpy())
     qh = (base.cpu().numpy() * 2.0).astype(np.float32)
     assert_close_topk(got, orc.topk(x, qh, orc.COSINE, 10, threads=8), x, qh, orc.COSINE)
+
+
+def test_guessed_start_equals_learnt_thresholds():
+    """Mid-size corpora start the live launch from thresholds GUESSED on a strided sample and verify them at the end."""
+    x, q = orc.synthetic(200_000, 256, 381), orc.synthetic(256, 256, 382)
+    with _f32_index(x) as ix:
+        c0 = ix.counters()
+        guessed = ix.search(q, 100, pk.COSINE)
+        c1 = ix.counters()
+        assert c1.fallback_queries == c0.fallback_queries, "a guess failed on benign data"
+        assert c1.kernel_launches - c0.kernel_launches <= 8   # prep, reset, sample scan, guess select, codes, live, deferred, select
+        ix.set_option("guess", 0)
+        learnt = ix.search(q, 100, pk.COSINE)
+        assert ix.counters().kernel_launches - c1.kernel_launches > 8
+    assert _same(guessed, learnt)
+    assert_close_topk(guessed, orc.topk(x, q, orc.COSINE, 100, threads=16), x, q, orc.COSINE)
+    x, q, scale, xc, qc = int8_space(200_000, 256, seed=383, nq=300)
+    with _i8_index(xc, scale) as ix:
+        guessed = ix.search(qc, 100, pk.L2)
+        assert ix.counters().fallback_queries == 0
+    assert_exact(guessed, orc.topk(xc, qc, orc.L2, 100, threads=16))
+
+
+def test_guess_too_tight_is_detected_and_redone():
+    # the only rows close to query 0 sit exactly on the sample's stride: the sample is far better than the corpus, the
+    # guessed threshold admits fewer than k rows, the end-of-search check notices and the search is redone
+    n, d, k = 150_001, 64, 100
+    x, q = orc.synthetic(n, d, 391), orc.synthetic(4, d, 392)
+    stride = n // 3968
+    rng = np.random.default_rng(39)
+    for j in range(60):
+        v = q[0] + rng.standard_normal(d).astype(np.float32) * 0.01
+        x[j * stride * 3] = v / np.linalg.norm(v)
+    with _f32_index(x) as ix:
+        got = ix.search(q, k, pk.COSINE)
+        assert ix.counters().fallback_queries > 0, "the too-tight guess went unnoticed"
+    assert_close_topk(got, orc.topk(x, q, orc.COSINE, k, threads=4), x, q, orc.COSINE)
+
+
+def test_guess_survives_sorted_insertion_order():
+    # rows inserted from worst to best for query 0: a prefix sample would be hopeless, the strided one is not
+    n, d = 120_000, 64
+    x, q = orc.synthetic(n, d, 395), orc.synthetic(5, d, 396)
+    x = np.ascontiguousarray(x[np.argsort(x @ q[0])])
+    with _f32_index(x) as ix:
+        got = ix.search(q, 50, pk.COSINE)
+        assert ix.counters().fallback_queries == 0
+    assert_close_topk(got, orc.topk(x, q, orc.COSINE, 50, threads=5), x, q, orc.COSINE)
