@@ -320,15 +320,24 @@ class Workload:
             uid = torch.tensor(list(pk.Comm.unique_id()) if rank == 0 else [0] * 128, dtype=torch.uint8, device=dev)
             dist.broadcast(uid, 0)
             self.comm = pk.Comm(local_rank, rank, world, bytes(uid.cpu().numpy().tolist()))
-        # config 5: membership bits over this shard's rows (Bernoulli(p), seed 0x5EED+2 over GLOBAL rows: SURVEY 8d),
-        # packed LSB-first into u64 words; the same bitmap for every query of the batch (context of an AND filter)
         self.bm_dev = self.bm_host = None
         if a.bitmap_density > 0:
-            member = np.random.default_rng(CORPUS_SEED + 2).random(a.rows) < a.bitmap_density
-            local = np.zeros(((r1 - r0 + 63) // 64) * 64, dtype=bool)
-            local[: r1 - r0] = member[r0:r1]
-            self.bm_host = np.packbits(local, bitorder="little").view(np.uint64).copy()
-            self.bm_dev = torch.from_numpy(self.bm_host.view(np.int64)).to(dev)
+            self.set_bitmap(a.bitmap_density)
+
+    def set_bitmap(self, density: float):
+        """config 5: membership bits over this shard's rows (Bernoulli(p), seed 0x5EED+2 over GLOBAL rows: SURVEY 8d),
+        packed LSB-first into u64 words; the same bitmap for every query of the batch (context of an AND filter).
+        density 0 removes it."""
+        self.bm_dev = self.bm_host = None
+        self.a.bitmap_density = density
+        if density <= 0:
+            return
+        a, r0, r1 = self.a, self.r0, self.r1
+        member = np.random.default_rng(CORPUS_SEED + 2).random(a.rows) < density
+        local = np.zeros(((r1 - r0 + 63) // 64) * 64, dtype=bool)
+        local[: r1 - r0] = member[r0:r1]
+        self.bm_host = np.packbits(local, bitorder="little").view(np.uint64).copy()
+        self.bm_dev = self.torch.from_numpy(self.bm_host.view(np.int64)).to(self.dev)
 
     def make_queries(self, step):
         q = gen_queries(self.torch, self.a.batch, self.a.dim, self.dev, step)
@@ -635,32 +644,119 @@ def cpu_baseline(a, corpus_sample: np.ndarray, queries: np.ndarray, metric_code:
             "pairs_per_s_per_core": nq * rows / dt / threads}, rows, out
 
 
-def sub_config(torch, pk, base_args, name, target, **over):
-    """One BASELINE config as a sub-record of the default line: its own index, device-resident value, e2e, roofline."""
+def _record(w, a, timed, e2e, target):
+    roof = w.roofline(timed)
+    return {"workload": workload_name(a), "n_gpus": w.world, "value": a.batch / (timed["ms_per_step"] * 1e-3), "unit": "queries/s",
+            "ms_per_step": timed["ms_per_step"], "steps": timed["steps"], "e2e": e2e["value"] if e2e else None, "target": target,
+            "roofline": {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms_per_step", "hbm_frac",
+                                              "tensor_frac", "tensor_frac_of_nominal", "peak_source",
+                                              "speedup_over_f32_streaming_roofline")},
+            "gpu_launches_per_step": (timed["c1"].kernel_launches - timed["c0"].kernel_launches + timed["merge_launches"])
+            / timed["steps"],
+            "search_stats": w.search_stats(timed)}
+
+
+def sub_config(torch, pk, base_args, name, target, dist=None, world=1, rank=0, **over):
+    """One BASELINE config as a sub-record of the default line: its own index (row-sharded over `world` ranks: every
+    rank calls this, rank 0 gets the record), device-resident value, e2e, roofline."""
     import copy
 
     a = copy.copy(base_args)
     for k, v in over.items():
         setattr(a, k, v)
-    a.opt, a.bitmap_density, a.force_simt = [], 0.0, False
+    a.opt, a.bitmap_density, a.force_simt, a.sample_rows = [], 0.0, False, 0
     try:
-        w = Workload(torch, pk, None, a, 1, 0, int(os.environ.get("LOCAL_RANK", "0")))
+        w = Workload(torch, pk, dist, a, world, rank, int(os.environ.get("LOCAL_RANK", "0")))
         timed = w.time_device(a.steps, 3, sample_clocks=False)
         e2e = w.time_e2e(max(5, a.steps // 2))
-        roof = w.roofline(timed)
-        rec = {"workload": workload_name(a), "value": a.batch / (timed["ms_per_step"] * 1e-3), "unit": "queries/s",
-               "ms_per_step": timed["ms_per_step"], "steps": a.steps, "e2e": e2e["value"], "target": target,
-               "roofline": {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms_per_step", "hbm_frac",
-                                                 "tensor_frac", "tensor_frac_of_nominal", "peak_source",
-                                                 "speedup_over_f32_streaming_roofline")},
-               "gpu_launches_per_step": (timed["c1"].kernel_launches - timed["c0"].kernel_launches) / a.steps,
-               "search_stats": w.search_stats(timed)}
+        rec = _record(w, a, timed, e2e, target) if rank == 0 else None
         w.close()
         del w
         torch.cuda.empty_cache()
         return rec
     except Exception as e:
         return {"workload": name, "error": repr(e)}
+
+
+def bitmap_leg(w, density, steps, target):
+    """BASELINE config 5 on the resident corpus of the main workload: the same searches AND a tag-filter row bitmap
+    (collective when sharded: every rank calls this)."""
+    import copy
+
+    keep = w.a
+    try:
+        w.a = copy.copy(keep)
+        w.set_bitmap(density)
+        timed = w.time_device(steps, 3, sample_clocks=False)
+        e2e = w.time_e2e(max(5, steps // 2))
+        return _record(w, w.a, timed, e2e, target) if w.rank == 0 else None
+    except Exception as e:
+        return {"workload": "C5", "error": repr(e)}
+    finally:
+        w.bm_dev = w.bm_host = None
+        w.a = keep
+
+
+def sharded_parity(torch, pk, dist, base_args, world, rank, local_rank, rows=2_000_000, nq_oracle=32):
+    """N-rank parity inside the driver's own scaling run: the first `rows` rows of the corpus row-sharded over the
+    `world` ranks, the WHOLE batch searched through pkv_search_sharded_device (scan + pack + ONE ncclAllGather + merge), and
+    `nq_oracle` of its queries compared with the oracle scanning the same rows on rank 0's host cores."""
+    import copy
+
+    a = copy.copy(base_args)
+    a.rows, a.opt, a.bitmap_density, a.force_simt, a.sample_rows = min(rows, base_args.rows), [], 0.0, False, 0
+    try:
+        w = Workload(torch, pk, dist, a, world, rank, local_rank)
+        got_all = tuple(t.clone() for t in w.step_device(w.q_dev[0]))
+        torch.cuda.synchronize()
+        shard_rows, kind = w.r1 - w.r0, w.ix.counters().last_scan_kind
+        rec = None
+        if rank == 0:
+            from oracle import oracle as orc
+
+            orc.build()
+            x = np.concatenate([gen_block(torch, b, BLOCK_ROWS, a.dim, w.dev)[off:off + n].cpu().numpy()
+                                for b, off, n in corpus_blocks(0, a.rows)])
+            sel = np.unique(np.linspace(0, a.batch - 1, min(nq_oracle, a.batch)).astype(np.int64))
+            qs = np.ascontiguousarray(w.q_dev[0].cpu().numpy()[sel])
+            omc = {"l2": orc.L2, "cosine": orc.COSINE, "dot": orc.DOT}[a.metric]
+            t0 = time.perf_counter()
+            want = orc.topk(x, qs, omc, a.k, threads=min(os.cpu_count() or 1, len(sel)))
+            dt = time.perf_counter() - t0
+            got = tuple(t.cpu().numpy()[sel] for t in got_all)
+            den = np.maximum(np.maximum(np.abs(want[1]), np.abs(1.0 - want[1]) if a.metric == "cosine" else 0.0), 1e-30)
+            rel = float(np.nanmax(np.abs(got[1] - want[1]) / den))
+            rec = {"checked": f"{world} ranks x {shard_rows} rows (first {a.rows} rows of the corpus), all {a.batch} queries through "
+                              f"pkv_search_sharded_device (scan kind {kind}); oracle: {len(sel)} of them over the same rows in {dt:.1f} s",
+                   "max_rel_err": rel, "within_1e-5": rel <= 1e-5, "ids_equal_frac": float(np.mean(got[0] == want[0])),
+                   "counts_equal": bool(np.array_equal(got[2], want[2])),
+                   "tolerance": "relative to max(|d|, |1-d|) for cosine (the score is 1-d), to |d| otherwise"}
+        w.close()
+        del w
+        torch.cuda.empty_cache()
+        return rec
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+class Watchdog:
+    """The multi-rank sub-records are extras: if one of them hangs a collective (a rank died, an exchange never
+    completed), rank 0 still prints the main line - marked - and every rank leaves."""
+
+    def __init__(self, seconds, rank, line):
+        self.line, self.rank = line, rank
+        self._t = threading.Timer(seconds + (0.0 if rank == 0 else 5.0), self._fire)
+        self._t.daemon = True
+        self._t.start()
+
+    def _fire(self):
+        if self.rank == 0:
+            self.line.setdefault("configs", {})["error"] = "multi-rank sub-records timed out; main line is complete"
+            print(json.dumps(self.line), flush=True)
+        os._exit(0)
+
+    def cancel(self):
+        self._t.cancel()
 
 
 # ------------------------------------------------------------------ our arm
@@ -693,40 +789,60 @@ def main():
     e2e = w.time_e2e(a.steps)
     sustained = w.time_sustained(a.sustain_seconds) if a.sustain_seconds > 0 else None
 
-    if rank != 0:
+    default_corpus = (a.rows == 10_000_000 and a.dim == 768 and a.batch == 256 and a.dtype == "f32" and a.metric == "cosine"
+                      and a.bitmap_density == 0 and not a.opt and not a.force_simt)
+    line = {}
+    if rank == 0:
+        roof = w.roofline(timed)
+        line = {
+            "metric": "queries/sec", "value": a.batch / (timed["ms_per_step"] * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": timed["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": config_dict(a, world, roof["algorithmic_bytes_per_row"]),
+            "clocks": timed["clocks"],
+            "e2e": e2e,
+            "gpu_launches": int(timed["c1"].kernel_launches - timed["c0"].kernel_launches) + timed["merge_launches"],
+            "roofline": roof,
+            "sustained": sustained,
+            "overflow_rescans": int(timed["c1"].fallback_queries - timed["c0"].fallback_queries),
+            # what the in-kernel machinery did per step (device counters of the searches in the timed region)
+            "search_stats": w.search_stats(timed),
+        }
+        if world == 1:
+            line["full_size_properties"] = w.full_size_properties(a.steps)
+        if world == 1 and not a.no_cpu and w.sample_host and a.bitmap_density == 0:
+            line["cpu_baseline"], line["parity"] = w.cpu_baseline_and_parity(a.cpu_seconds)
+
+    # ---- more than one GPU: BASELINE configs 4 and 5 (the ones quoted on 8 GPUs) and an N-rank parity leg as
+    # sub-records of the scaling line, so that the driver's own 2/4/8-GPU runs hold them.  Collective: every rank runs
+    # them; a watchdog keeps a stuck extra from costing the main line.
+    if world > 1 and default_corpus and not a.no_configs:
+        dog = Watchdog(420.0, rank, line)
+        steps2 = max(10, min(a.steps, 30))
+        c5 = bitmap_leg(w, 0.1, steps2, "config 5: vector top-k AND tag-filter bitmap (density 0.1), 10M corpus")
         w.close()
+        del w
+        torch.cuda.empty_cache()
+        par = sharded_parity(torch, pk, dist, a, world, rank, local_rank)
+        c4 = sub_config(torch, pk, a, "C4", "config 4: 50Mx512 fp16 (OpenCLIP ViT-B/32 shape), batch 4096, row-sharded",
+                        dist=dist, world=world, rank=rank, rows=50_000_000, dim=512, dtype="f16", metric="cosine", batch=4096,
+                        steps=5)
+        dog.cancel()
+        if rank == 0:
+            line["parity"] = par
+            line["configs"] = {"C4": c4, "C5": c5}
+    else:
+        w.close()
+        del w
+        torch.cuda.empty_cache()
+    if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    roof = w.roofline(timed)
-    line = {
-        "metric": "queries/sec", "value": a.batch / (timed["ms_per_step"] * 1e-3), "unit": "queries/s", "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": timed["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": config_dict(a, world, roof["algorithmic_bytes_per_row"]),
-        "clocks": timed["clocks"],
-        "e2e": e2e,
-        "gpu_launches": int(timed["c1"].kernel_launches - timed["c0"].kernel_launches) + timed["merge_launches"],
-        "roofline": roof,
-        "sustained": sustained,
-        "overflow_rescans": int(timed["c1"].fallback_queries - timed["c0"].fallback_queries),
-        # what the in-kernel machinery did per step (device counters of the searches in the timed region)
-        "search_stats": w.search_stats(timed),
-    }
-    if world == 1:
-        line["full_size_properties"] = w.full_size_properties(a.steps)
-    if not a.no_cpu and w.sample_host and a.bitmap_density == 0:
-        line["cpu_baseline"], line["parity"] = w.cpu_baseline_and_parity(a.cpu_seconds)
-    w.close()
-    del w
-    torch.cuda.empty_cache()
-
     # ---- BASELINE configs 2 and 3 as sub-records of the default line (their targets: >= 70 % of the HBM roofline of an
     # f32-streaming scan = 382 k queries/s; >= 40 % of the int8 tensor peak)
-    default_workload = (world == 1 and a.rows == 10_000_000 and a.dim == 768 and a.batch == 256 and a.dtype == "f32"
-                        and a.metric == "cosine" and a.bitmap_density == 0 and not a.opt and not a.force_simt)
-    if default_workload and not a.no_configs:
+    if world == 1 and default_corpus and not a.no_configs:
         a.sample_rows = 0
         steps2 = max(10, min(a.steps, 40))
         line["configs"] = {

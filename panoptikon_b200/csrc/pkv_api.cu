@@ -323,7 +323,7 @@ static bool live_int8_ok(const Index &ix, int nq) {
 // Queries already on the device in caller layout; outputs to device buffers.
 static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_qraw, int nq,
                         const pkv_search_params &p, const uint64_t *d_bitmap, int64_t *d_ids, float *d_dist,
-                        int32_t *d_counts) {
+                        int32_t *d_counts, bool allow_guess = true) {
     const int64_t N = ix.sealed_rows;
     const int k = p.k;
     PKV_TRY(launch_prep_queries(ix, ws, d_qraw, nq, p.query_dtype, s));
@@ -403,21 +403,39 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // (which is what splits overflowing ranges).  Bitmap searches stay careful until every query has a
     // threshold: their candidate rate is unknown until the first members are seen.
     static const bool trace_env = getenv("PKV_TRACE") != nullptr;
+    const int kind_code =
+        r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
     bool optimistic = ix.opt.optimistic && !d_bitmap && !trace_env;
     bool allow_live = r.live_capable;
-    // Guessed start (mid-size corpora): instead of LEARNING the thresholds chunk by chunk, guess them - the
-    // guess_rank-th best of a strided sample of the corpus, a real row's distance that about guess_factor * k rows
-    // of the corpus beat - start the candidate lists empty, run ONE live launch over every row, and verify at the end:
-    // a query that found k rows under its guess has provably missed nothing; otherwise the search is redone on the
-    // learning schedule.  The sample holds >= 4 rows better than the guess, so a miss needs the corpus' best rows to be
-    // ~40x rarer than the sample says (adversarial insertion orders are what the strided sample defends against).
+    // Guessed start: instead of LEARNING the thresholds chunk by chunk, guess them - the r-th best of a strided sample
+    // of the corpus (a real row's distance that about r * N / sample rows of the corpus beat) - start the candidate
+    // lists empty, run ONE live launch over every row, and verify at the end: a query that found k rows under its guess
+    // has provably missed nothing; the others (rare, see below) are searched again on the learning schedule.
+    // r: with x = k * sample / N sample rows expected among the corpus' true top-k, the guess is too tight for a query
+    // (fewer than k corpus rows beat the sample's r-th best) with probability P[Poisson(x) >= r]; r is the smallest rank
+    // that keeps this below guess_miss_ppm (1e-4: one query in 10 000, i.e. one batch of 256 in 40 pays a second,
+    // small search).  Measured on B200 (profiles/README.md): the tighter the guess the faster - 1M rows r = 4 / 6 / 10 /
+    // 16: 215 k / 193 k / 167 k / 147 k queries/s; 10M rows r = 5 / 10: 78 k / 73 k (chunked prefix: 74 k), r = 20
+    // overflows the candidate lists (the burst before the thresholds tighten) - hence the cap on the admitted rows.
     int guess_rank = 0;
-    if (allow_live && ix.opt.guess && optimistic && ix.sample_rows > 0 && ix.sample_of_rows == N &&
+    if (allow_guess && allow_live && ix.opt.guess && optimistic && ix.sample_rows > 0 && ix.sample_of_rows == N &&
         N <= ix.opt.guess_max_rows && ix.sample_rows <= r.safe_rows && ix.opt.live_start_rows == 0) {
-        const double want = (double)ix.opt.guess_factor * (double)k * (double)ix.sample_rows / (double)N;
-        guess_rank = (int)(want + 0.5);
-        if (guess_rank > k) guess_rank = k;
-        if (guess_rank < 4) guess_rank = 0;
+        const double x = (double)k * (double)ix.sample_rows / (double)N;
+        int rank;
+        if (ix.opt.guess_factor > 0) {   // explicit tightness (experiments): this many times k rows beat the guess
+            rank = (int)((double)ix.opt.guess_factor * x + 0.5);
+        } else {
+            const double eps = (double)ix.opt.guess_miss_ppm * 1e-6;
+            double term = exp(-x), cdf = 0.0;
+            for (rank = 0; rank < 4096; ++rank) {
+                if (rank >= 2 && 1.0 - cdf <= eps) break;
+                cdf += term;
+                term *= x / (double)(rank + 1);
+            }
+        }
+        // the lists must survive the burst of rows a guess admits before the in-kernel feedback tightens it
+        const double admitted = (double)rank * (double)N / (double)ix.sample_rows;
+        if (rank >= 2 && rank <= ix.sample_rows / 4 && admitted <= 16000.0) guess_rank = rank;
     }
 restart:
     int64_t pos = 0;
@@ -497,11 +515,60 @@ restart:
         if (guess_rank > 0 && !ws.h_status->sticky_overflow && !ws.h_status->defer_overflow &&
             ws.h_status->min_filled < (uint32_t)(N < k ? N : k)) {
             // some query found fewer than k rows under its guessed threshold: the guess was too tight for it.
-            // Redo the search with learnt thresholds (still optimistic, still live).
-            r.depth_overflows++;
+            // The results of all other queries are final (they are written); the few that failed are searched again
+            // with learnt thresholds as a small batch of their own and their rows overwritten.
             guess_rank = 0;
-            PKV_TRY(launch_reset_state(ws, nq, s));
-            goto restart;
+            std::vector<int32_t> cnt((size_t)nq);
+            PKV_CUDA(cudaMemcpyAsync(cnt.data(), d_counts, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, s));
+            PKV_CUDA(cudaStreamSynchronize(s));
+            std::vector<int> failed;
+            for (int q = 0; q < nq; ++q)
+                if (cnt[(size_t)q] < (int32_t)(N < k ? N : k)) failed.push_back(q);
+            if (!r.outputs_written || failed.empty() || failed.size() > 16) {
+                r.depth_overflows++;  // (many misses: the sample misrepresents the corpus - learn the thresholds)
+                PKV_TRY(launch_reset_state(ws, nq, s));
+                goto restart;
+            }
+            const int nf = (int)failed.size();
+            const size_t qbytes = (size_t)ix.dim * (size_t)elem_size(p.query_dtype);
+            uint8_t *d_tmp = nullptr;
+            const size_t off_ids = (qbytes * (size_t)nf + 255) / 256 * 256, off_dist = off_ids + sizeof(int64_t) * (size_t)nf * k,
+                         off_cnt = off_dist + sizeof(float) * (size_t)nf * k;
+            PKV_CUDA(cudaMalloc((void **)&d_tmp, off_cnt + sizeof(int32_t) * (size_t)nf));
+            for (int i = 0; i < nf; ++i)
+                cudaMemcpyAsync(d_tmp + qbytes * (size_t)i, (const uint8_t *)d_qraw + qbytes * (size_t)failed[(size_t)i], qbytes,
+                                cudaMemcpyDeviceToDevice, s);
+            // (the workspace is free again: every launch of this search has completed)
+            const int saved_launches = r.launches, saved_scan = r.scan_launches;
+            const double saved_ms = r.scan_ms;
+            const SearchStatus st0 = *ws.h_status;
+            int rc = search_batch(ix, ws, s, d_tmp, nf, p, nullptr, (int64_t *)(d_tmp + off_ids), (float *)(d_tmp + off_dist),
+                                  (int32_t *)(d_tmp + off_cnt), /*allow_guess=*/false);
+            if (rc == PKV_OK) {
+                for (int i = 0; i < nf; ++i) {
+                    const size_t q = (size_t)failed[(size_t)i];
+                    cudaMemcpyAsync(d_ids + q * k, d_tmp + off_ids + sizeof(int64_t) * (size_t)i * k, sizeof(int64_t) * k,
+                                    cudaMemcpyDeviceToDevice, s);
+                    cudaMemcpyAsync(d_dist + q * k, d_tmp + off_dist + sizeof(float) * (size_t)i * k, sizeof(float) * k,
+                                    cudaMemcpyDeviceToDevice, s);
+                    cudaMemcpyAsync(d_counts + q, d_tmp + off_cnt + sizeof(int32_t) * (size_t)i, sizeof(int32_t),
+                                    cudaMemcpyDeviceToDevice, s);
+                }
+                if (cudaStreamSynchronize(s) != cudaSuccess) rc = fail(PKV_ERR_CUDA, "guess repair: copy failed");
+            }
+            cudaFree(d_tmp);
+            if (rc != PKV_OK) return rc;
+            // the inner search has added its own figures to the index counters; this (outer) search adds the rest
+            ix.n_fallback += nf;
+            ix.n_launches += saved_launches + 3 * nf + 1;
+            ix.n_scan_launches += saved_scan;
+            ix.n_live_refreshes += st0.live_refreshes;
+            ix.n_live_skips += st0.live_skips;
+            ix.n_rescored += st0.rescored;
+            ix.n_deferred += st0.deferred;
+            g_last.scan_ms += saved_ms;
+            g_last.kind = kind_code;
+            return PKV_OK;
         }
         if (ws.h_status->sticky_overflow) {
             guess_rank = 0;
@@ -552,7 +619,7 @@ restart:
     ix.n_scan_launches += r.scan_launches;
     ix.n_fallback += r.depth_overflows;
     g_last.scan_ms += r.scan_ms;
-    g_last.kind = r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
+    g_last.kind = kind_code;
     return PKV_OK;
 }
 
@@ -1343,11 +1410,13 @@ int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {
     else if (!strcmp(name, "live_refresh")) ix.opt.live_refresh = (int)value;
     else if (!strcmp(name, "img8_fused")) ix.opt.img8_fused = (int)value;
     else if (!strcmp(name, "img8_defer")) ix.opt.img8_defer = (int)value;
+    else if (!strcmp(name, "img8_epi")) ix.opt.img8_epi = (int)value;
     else if (!strcmp(name, "live_start_rows")) ix.opt.live_start_rows = value;
     else if (!strcmp(name, "live_min_rows")) ix.opt.live_min_rows = value;
     else if (!strcmp(name, "guess")) ix.opt.guess = (int)value;
     else if (!strcmp(name, "guess_max_rows")) ix.opt.guess_max_rows = value;
     else if (!strcmp(name, "guess_factor")) ix.opt.guess_factor = (int)value;
+    else if (!strcmp(name, "guess_miss_ppm")) ix.opt.guess_miss_ppm = (int)value;
     else return fail(PKV_ERR_INVALID, "unknown option '%s'", name);
     return PKV_OK;
 }

@@ -239,12 +239,15 @@ struct Options {
     int img8_defer = 1;              // int8-image path: pairs inside the filter's error band wait for the final thresholds
     int img8_fused = 1;              // int8-image path, exact re-scoring by warps of the scan kernel itself: 0 never
                                      // (no live launches either), 1 in live launches, 2 in every launch
+    int img8_epi = 1;                // int8-image epilogue: survivors of the warp-wide bound are culled with the exact per-pair
+                                     // bound in registers before they are held (0: at flush time, from global row figures)
     int64_t live_start_rows = 0;     // rows scanned on the chunked schedule before the live launch (0 = auto)
     int guess = 1;                   // start the live launch from thresholds GUESSED on a strided sample (verified at the
-                                     // end: a query that did not find k rows under its guess redoes the search)
-    int64_t guess_max_rows = 1600000; // ... for corpora up to this many rows (the sample must hold a few rows better
-                                     // than the guess: beyond, the chunked prefix learns the thresholds)
-    int guess_factor = 16;           // the guess aims at this many times k rows beating it
+                                     // end: a query that did not find k rows under its guess is searched again)
+    int64_t guess_max_rows = 24000000; // ... for corpora up to this many rows (beyond, even the 2nd best of the sample
+                                     // admits more rows than the candidate lists survive: the chunked prefix learns)
+    int guess_miss_ppm = 100;        // acceptable probability (parts per million, per query) that a guess is too tight
+    int guess_factor = 0;            // > 0: explicit tightness instead - this many times k rows of the corpus beat the guess
     int64_t live_min_rows = 600000;  // live = 1: only when the live launch would cover at least this many rows (2 = always)
 };
 

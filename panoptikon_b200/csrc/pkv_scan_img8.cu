@@ -64,6 +64,10 @@ struct ImgArgs {
                              // filter's error band (and, fused, whatever the ring cannot take) are parked with their dot
                              // product and re-checked against the FINAL thresholds at the end of the search
     int rows_f16;            // stored rows are fp16 (f16 index), else f32
+    int park_lean;           // parked pairs carry (row, dot) only: the deferred pass reads the row figures itself
+    int epi_exact;           // the epilogue culls with the EXACT per-pair bound in registers (row figures shuffled from the
+                             // lane that prefetched them) before a pair enters the hold list: the flush has no
+                             // dependent global load left and sees ~half the entries
 };
 
 struct ImgShared {
@@ -75,7 +79,7 @@ struct ImgShared {
     uint32_t ring_head;  // tickets handed to producers (epilogue lanes)
     uint32_t ring_tail;  // tickets handed to consumers (re-scoring warps)
     uint32_t epi_done;   // epilogue warps that have pushed their last survivor
-    uint32_t hold_cnt[EPI_WARPS];
+    uint32_t hold_cnt[EPI_WARPS];  // (img8_epi = 0 only: the atomically filled hold lists of round 1)
     uint64_t rs_bar[RS_WARPS][RS_SLOTS];  // completion of the re-scoring warps' row copies
     alignas(16) float4 qm[QM_CTA];  // per query {1/s_q, |e_q|/s_q, |q|/s_q, |q|^2} (fixed for the launch)
     float thr[QM_CTA];              // per query: filter threshold (live mode: refreshed tile by tile)
@@ -177,22 +181,33 @@ __device__ __forceinline__ bool ring_try_push(ImgShared *sh, uint32_t row, uint3
 }
 
 // One pre-filter survivor: exact per-pair bound, membership, then hand the row on for exact re-scoring.
+// `col` bit 31 set: the pair already passed the per-pair bound in the epilogue's registers (epi_exact) and bit 30 says
+// whether it is a LIKELY candidate; nothing is left to check but membership.
+constexpr uint32_t COL_CHECKED = 0x80000000u, COL_LIKELY = 0x40000000u;
 template <int METRIC>
-__device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, int qbase, int col, int d, uint32_t row,
+__device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, int qbase, uint32_t colw, int d, uint32_t row,
                                           ImgShared *sh) {
+    const int col = (int)(colw & 0xffffu);
     const int q = qbase + col;
     if (q >= a.nq || row >= a.row_end) return;
-    const float4 m = __ldg(im.row_meta + row);
-    float x1, x2;
-    row_figures<METRIC>(m, x1, x2);
-    float4 qc;
-    float qs;
-    query_consts<METRIC>(sh->qm[col], *(volatile const float *)&sh->thr[col], qc, qs);
-    float lead;
-    const float b = pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x, &lead);
-    if ((float)d < b) return;  // NaN bound (non-finite row or query): kept
+    bool likely;
+    float4 m;
+    const bool checked = (colw & COL_CHECKED) != 0;
+    if (checked) {
+        likely = (colw & COL_LIKELY) != 0;
+    } else {
+        m = __ldg(im.row_meta + row);
+        float x1, x2;
+        row_figures<METRIC>(m, x1, x2);
+        float4 qc;
+        float qs;
+        query_consts<METRIC>(sh->qm[col], *(volatile const float *)&sh->thr[col], qc, qs);
+        float lead;
+        const float b = pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x, &lead);
+        if ((float)d < b) return;  // NaN bound (non-finite row or query): kept
+        likely = !((float)d < lead);  // the approximate score beats the threshold (or the pair is unfilterable)
+    }
     if (!topk_member(a.topk, q, row)) return;
-    const bool likely = !((float)d < lead);  // the approximate score beats the threshold (or the pair is unfilterable)
     if (im.fused) {
         if (!im.defer) {
             ring_push(sh, row, (uint32_t)col, d);
@@ -204,11 +219,14 @@ __device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, 
         if (slot < im.pend.cap) im.pend.rows[(size_t)q * im.pend.cap + slot] = row;
         return;
     }
+    // parked: the deferred pass re-checks with the row figures (a pre-checked pair loads them only now - the load is in
+    // flight together with the list's atomic, not ahead of it)
+    if (checked && im.dlist.meta) m = __ldg(im.row_meta + row);
     const uint32_t slot = atomicAdd(im.dlist.cnt + q, 1u);
     if (slot < im.dlist.cap) {
         im.dlist.rows[(size_t)q * im.dlist.cap + slot] = row;
         im.dlist.dots[(size_t)q * im.dlist.cap + slot] = d;
-        im.dlist.meta[(size_t)q * im.dlist.cap + slot] = m;
+        if (im.dlist.meta) im.dlist.meta[(size_t)q * im.dlist.cap + slot] = m;
     }
 }
 
@@ -431,7 +449,7 @@ __device__ __forceinline__ void rescore_loop(const ScanArgs &a, const ImgArgs &i
                 if (slot < im.dlist.cap) {
                     im.dlist.rows[(size_t)q * im.dlist.cap + slot] = row;
                     im.dlist.dots[(size_t)q * im.dlist.cap + slot] = d;
-                    im.dlist.meta[(size_t)q * im.dlist.cap + slot] = __ldg(im.row_meta + row);
+                    if (im.dlist.meta) im.dlist.meta[(size_t)q * im.dlist.cap + slot] = __ldg(im.row_meta + row);
                 }
             }
             continue;
@@ -491,6 +509,11 @@ __device__ __forceinline__ void rescore_loop(const ScanArgs &a, const ImgArgs &i
     if (lane == 0 && done) atomicAdd(&a.topk.status->rescored, done);
 }
 
+// ---- the epilogue warp's hold list: pre-filter survivors wait in shared memory (this warp's own slots) until ~32 of
+// them can be handled lane-parallel.
+// img8_epi = 0 (round 1): divergent per-pair calls fill the list through a shared-memory atomic; the flush checks every
+// entry against the exact per-pair bound (row figures from global memory) and parks / queues it - two dependent global
+// round trips inside the accumulator hand-off loop.
 template <int METRIC>
 __device__ __noinline__ void hold_img(const ScanArgs &a, const ImgArgs &im, int qbase, int col, int d, uint32_t row,
                                       ImgShared *sh, int ew) {
@@ -500,7 +523,7 @@ __device__ __noinline__ void hold_img(const ScanArgs &a, const ImgArgs &im, int 
         sh->hold_dot[ew][slot] = d;
         sh->hold_col[ew][slot] = (uint32_t)col;
     } else {
-        consider_img<METRIC>(a, im, qbase, col, d, row, sh);
+        consider_img<METRIC>(a, im, qbase, (uint32_t)col, d, row, sh);
     }
 }
 
@@ -512,10 +535,58 @@ __device__ __forceinline__ void flush_img(const ScanArgs &a, const ImgArgs &im, 
     if (cnt < min_cnt) return;
     const uint32_t n = cnt < HOLD_CAP ? cnt : HOLD_CAP;
     for (uint32_t e = lane; e < n; e += 32)
-        consider_img<METRIC>(a, im, qbase, (int)sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
+        consider_img<METRIC>(a, im, qbase, sh->hold_col[ew][e], sh->hold_dot[ew][e], sh->hold_row[ew][e], sh);
     __syncwarp();
     if (lane == 0) sh->hold_cnt[ew] = 0;
     __syncwarp();
+}
+
+// img8_epi = 1 (round 2): the list is filled warp-uniformly (ballot + prefix popcount, the fill count is a register)
+// with pairs that already passed the exact per-pair bound in registers; the flush has no dependent global load left.
+// A pair that must be PARKED (outside the in-kernel re-scorer's reach) only ISSUES the atomic that reserves its slot in
+// the query's parked list; the three stores that need the slot are made at the next flush (or at the end of the scan),
+// when the atomic has long returned: the epilogue warp never waits for a global round trip between two accumulators.
+struct ParkPending {
+    uint32_t slot, row;
+    int d, q;  // q < 0: nothing pending
+};
+
+__device__ __forceinline__ void park_complete(const ImgArgs &im, ParkPending &pp) {
+    if (pp.q >= 0) {
+        if (pp.slot < im.dlist.cap) {
+            im.dlist.rows[(size_t)pp.q * im.dlist.cap + pp.slot] = pp.row;
+            im.dlist.dots[(size_t)pp.q * im.dlist.cap + pp.slot] = pp.d;
+        }
+        pp.q = -1;
+    }
+}
+
+template <int METRIC>
+__device__ __noinline__ ParkPending flush_held(const ScanArgs &a, const ImgArgs &im, int qbase, ImgShared *sh, int ew, int lane,
+                                               uint32_t n, ParkPending pp) {
+    __syncwarp();
+    for (uint32_t base = 0; base < n; base += 32) {
+        park_complete(im, pp);  // (a second round of one flush waits for the first round's atomics: n > 32 is rare)
+        const uint32_t e = base + (uint32_t)lane;
+        if (e < n) {
+            const uint32_t colw = sh->hold_col[ew][e], row = sh->hold_row[ew][e];
+            const int d = sh->hold_dot[ew][e];
+            const int col = (int)(colw & 0xffffu), q = qbase + col;
+            const bool parkable = (colw & COL_CHECKED) && im.fused && im.defer && im.park_lean;
+            if (!parkable) {
+                consider_img<METRIC>(a, im, qbase, colw, d, row, sh);  // every other mode: the synchronous path
+            } else if (q < a.nq && row < a.row_end && topk_member(a.topk, q, row)) {
+                if (!((colw & COL_LIKELY) && ring_try_push(sh, row, (uint32_t)col, d))) {
+                    pp.slot = atomicAdd(im.dlist.cnt + q, 1u);  // issued now, consumed at the next flush
+                    pp.row = row;
+                    pp.d = d;
+                    pp.q = q;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    return pp;
 }
 
 // non-negative floats order like their bit patterns: hardware warp min/max on the unsigned view
@@ -564,9 +635,9 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             tc::mbar_init(&sh->tmem_full[b], 1);
             tc::mbar_init(&sh->tmem_empty[b], NCTA * EPI_USED);
         }
-        for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
         for (int w = 0; w < RS_WARPS; ++w)
             for (int b = 0; b < RS_SLOTS; ++b) tc::mbar_init(&sh->rs_bar[w][b], 1);
+        for (int w = 0; w < EPI_WARPS; ++w) sh->hold_cnt[w] = 0;
         sh->ring_head = 0;
         sh->ring_tail = 0;
         sh->epi_done = 0;
@@ -715,6 +786,9 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         const int col0 = (ew >> 2) * 32;       // accumulator columns = rows of the tile
         const int qcol = quarter * 32 + lane;  // this thread's query within the CTA
         uint32_t buf = 0, bph = 0;
+        uint32_t hold_n = 0;  // entries in this warp's hold list (warp-uniform; img8_epi = 1)
+        ParkPending pp{0u, 0u, 0, -1};
+        const uint32_t lt_mask = (1u << lane) - 1u;
         // lane j prefetches the figures of row col0 + j (the warp's 32 rows of the tile)
         uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
         bool row_ok = seq < ntiles && nrow < a.row_end;
@@ -739,9 +813,17 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                 x2hi = warp_max_nn(row_ok ? x2 : 0.f);
             }
             const float vhi = warp_max_nn(m.y), whi = warp_max_nn(m.z), uhi = warp_max_nn(m.x);
+            const float4 mc = m;  // figures of row col0 + lane of THIS tile (exact per-pair bounds below)
             nrow = a.row_begin + (tile + nseq) * TILE_N + col0 + lane;
             row_ok = tile + nseq < ntiles && nrow < a.row_end;
             m = row_ok ? __ldg(im.row_meta + nrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                // ... and the figures of the tile after next are pulled into L2 now: the load above then never waits for
+                // DRAM - with 32 epilogue warps per accumulator, ONE slow DRAM access per tile stalls the whole hand-off
+                const uint32_t prow = a.row_begin + (tile + 3 * nseq) * TILE_N + col0 + lane;
+                if (tile + 3 * nseq < ntiles && prow < a.row_end && (lane & 7) == 0)  // one request per 128-byte line
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(im.row_meta + prow));
+            }
             float bf = pair_bound<METRIC>(qc, qs, x1lo, x1hi, x2lo, x2hi, vhi, whi, uhi);
             bf = fminf(fmaxf(bf, -BOUND_CLAMP), BOUND_CLAMP);  // NaN -> -clamp: keep everything
             const int bound = real_q ? __float2int_rd(bf) : (int)BOUND_CLAMP;
@@ -757,20 +839,108 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                 else tc::mbar_arrive(&sh->tmem_empty[buf]);
             }
             if (++buf == NBUF) { buf = 0; bph ^= 1; }
-            // sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once
-            int any = 0;
+            if (!im.epi_exact) {
+                // round 1: sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once per lane
+                int any = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) any |= bound - (int)v[j] - 1;
-            if (any < 0) {
+                for (int j = 0; j < 32; ++j) any |= bound - (int)v[j] - 1;
+                if (any < 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int d = (int)v[j];
+                        if (d >= bound) hold_img<METRIC>(a, im, qbase, qcol, d, row_first + j, sh, ew);
+                    }
+                }
+                flush_img<METRIC>(a, im, qbase, sh, ew, lane, HOLD_FLUSH);
+                continue;
+            }
+            // round 2.  The largest of the lane's 32 dot products against the bound (3-input max: 16 instructions), one
+            // branch for the whole warp
+            int vmax = (int)v[0];
+#pragma unroll
+            for (int j = 1; j < 31; j += 2) vmax = __vimax3_s32(vmax, (int)v[j], (int)v[j + 1]);
+            vmax = max(vmax, (int)v[31]);
+            if (__any_sync(0xffffffffu, vmax >= bound)) {
+                // straight-line, predicated: each lane (query) notes how many of its 32 rows pass and which was the last
+                int n = 0, ej = 0, ed = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int d = (int)v[j];
-                    if (d >= bound) hold_img<METRIC>(a, im, qbase, qcol, d, row_first + j, sh, ew);
+                    if ((int)v[j] >= bound) {
+                        ej = j;
+                        ed = (int)v[j];
+                        ++n;
+                    }
+                }
+                int fj = ej, fd = ed;
+                const int nmax = __reduce_max_sync(0xffffffffu, n);
+                if (nmax >= 2) {  // some lane has two: the FIRST of each lane as well
+#pragma unroll
+                    for (int j = 31; j >= 0; --j) {
+                        if ((int)v[j] >= bound) {
+                            fj = j;
+                            fd = (int)v[j];
+                        }
+                    }
+                }
+                if (nmax <= 2) {
+                    // <= 2 rounds: bound THIS pair exactly - the figures of row j sit in lane j (mc) - and append what
+                    // is left, warp-uniformly (ballot + prefix popcount: no atomics, no divergent calls)
+                    for (int round = 0; round < nmax; ++round) {
+                        const int rj = round == 0 ? ej : fj, rd = round == 0 ? ed : fd;
+                        bool pass = n > round;
+                        float4 mj;
+                        mj.x = __shfl_sync(0xffffffffu, mc.x, rj);
+                        mj.y = __shfl_sync(0xffffffffu, mc.y, rj);
+                        mj.z = __shfl_sync(0xffffffffu, mc.z, rj);
+                        mj.w = __shfl_sync(0xffffffffu, mc.w, rj);
+                        uint32_t colw = (uint32_t)qcol | COL_CHECKED;
+                        if (pass) {
+                            float x1, x2, lead;
+                            row_figures<METRIC>(mj, x1, x2);
+                            const float b = pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, mj.y, mj.z, mj.x, &lead);
+                            if ((float)rd < b) pass = false;  // NaN bound (non-finite row or query): kept
+                            if (!((float)rd < lead)) colw |= COL_LIKELY;
+                        }
+                        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                        if (pass) {
+                            const uint32_t slot = hold_n + (uint32_t)__popc(mask & lt_mask);
+                            sh->hold_row[ew][slot] = row_first + (uint32_t)rj;
+                            sh->hold_dot[ew][slot] = rd;
+                            sh->hold_col[ew][slot] = colw;
+                        }
+                        hold_n += (uint32_t)__popc(mask);
+                        if (hold_n > (uint32_t)(HOLD_CAP - 32)) {  // the next round may add 32 more
+                            pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
+                            hold_n = 0;
+                        }
+                    }
+                } else {
+                    // three or more rows of one query in one 32-row slice: survivors are DENSE (a chunk scanned with
+                    // a threshold learnt from few rows) - the round-1 list, filled through its shared-memory counter and
+                    // emptied lane-parallel right away, is the cheaper tool there
+                    if (hold_n) {
+                        pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
+                        hold_n = 0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int d = (int)v[j];
+                        if (d >= bound) hold_img<METRIC>(a, im, qbase, qcol, d, row_first + j, sh, ew);
+                    }
+                    flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
                 }
             }
-            flush_img<METRIC>(a, im, qbase, sh, ew, lane, HOLD_FLUSH);
+            if (hold_n >= (uint32_t)HOLD_FLUSH) {
+                pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
+                hold_n = 0;
+            }
         }
-        flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
+        if (im.epi_exact) {
+            if (hold_n) pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
+            park_complete(im, pp);
+        } else {
+            flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
+        }
         __syncwarp();
         if (lane == 0) {  // this warp has published its last survivor
             __threadfence_block();
@@ -826,7 +996,7 @@ __global__ void __launch_bounds__(256) rescore_deferred_kernel(const ScanArgs a,
         if (e < n) {
             row = im.dlist.rows[(size_t)q * im.dlist.cap + e];
             const int d = im.dlist.dots[(size_t)q * im.dlist.cap + e];
-            const float4 m = im.dlist.meta[(size_t)q * im.dlist.cap + e];
+            const float4 m = im.dlist.meta ? im.dlist.meta[(size_t)q * im.dlist.cap + e] : __ldg(im.row_meta + row);
             float x1, x2;
             row_figures<METRIC>(m, x1, x2);
             keep = !((float)d < pair_bound<METRIC>(qc, qs, x1, x1, x2, x2, m.y, m.z, m.x));
@@ -839,13 +1009,31 @@ __global__ void __launch_bounds__(256) rescore_deferred_kernel(const ScanArgs a,
             const uint32_t r = __shfl_sync(0xffffffffu, row, src);
             const uint8_t *rb = (const uint8_t *)a.data + (size_t)r * (size_t)a.pitch_bytes;
             float acc = 0.f, nrm = 0.f;
+            // all of the row's loads are issued before the first is consumed (one memory latency per gathered row instead
+            // of one per 512 bytes); the element order of the sums is unchanged
             if (!ROWS_F16) {
                 const float4 *rp = (const float4 *)rb;
-                for (int j = lane; j < nvec; j += 32) acc_f4<METRIC>(__ldg(rp + j), s_q[j], acc, nrm);
+                float4 rv[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    if (lane + it * 32 < nvec) rv[it] = __ldg(rp + lane + it * 32);
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    if (lane + it * 32 < nvec) acc_f4<METRIC>(rv[it], s_q[lane + it * 32], acc, nrm);
+                for (int j = lane + 256; j < nvec; j += 32) acc_f4<METRIC>(__ldg(rp + j), s_q[j], acc, nrm);
             } else {
                 const uint4 *rp = (const uint4 *)rb;
                 const int nvec8 = a.dim_pad >> 3;
-                for (int j = lane; j < nvec8; j += 32) acc_h8<METRIC>(__ldg(rp + j), s_q[2 * j], s_q[2 * j + 1], acc, nrm);
+                uint4 rv[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    if (lane + it * 32 < nvec8) rv[it] = __ldg(rp + lane + it * 32);
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int j = lane + it * 32;
+                    if (j < nvec8) acc_h8<METRIC>(rv[it], s_q[2 * j], s_q[2 * j + 1], acc, nrm);
+                }
+                for (int j = lane + 128; j < nvec8; j += 32) acc_h8<METRIC>(__ldg(rp + j), s_q[2 * j], s_q[2 * j + 1], acc, nrm);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -1148,6 +1336,9 @@ static ImgArgs img_args(const Index &ix, const ScanArgs &a, Workspace &ws) {
     im.fused = (ix.opt.img8_fused >= 2 || a.topk.live) ? 1 : 0;
     im.defer = a.topk.defer;
     im.rows_f16 = ix.dtype == PKV_F16 ? 1 : 0;
+    im.epi_exact = ix.opt.img8_epi;
+    im.park_lean = ix.opt.img8_epi ? 1 : 0;
+    if (im.park_lean) im.dlist.meta = nullptr;
     return im;
 }
 

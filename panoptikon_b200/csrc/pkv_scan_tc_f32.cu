@@ -448,9 +448,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const ScanArgs a, const Pe
         float acc = 0.f, nrm = 0.f;
         if (!ROWS_F16) {
             const float4 *rp = (const float4 *)rb;
-            for (int j = lane; j < nvec; j += 32) {
-                const float4 av = __ldg(rp + j);
-                const float4 qv = s_q[j];
+            auto body = [&](const float4 av, const float4 qv) {
                 if (METRIC == PKV_L2) {
                     float t;
                     t = av.x - qv.x; acc = fmaf(t, t, acc);
@@ -469,7 +467,17 @@ __global__ void __launch_bounds__(256) rescore_kernel(const ScanArgs a, const Pe
                     nrm = fmaf(av.z, av.z, nrm);
                     nrm = fmaf(av.w, av.w, nrm);
                 }
-            }
+            };
+            // the row's first 8 loads per lane (D <= 1024: all of them) are issued before any is consumed: one memory
+            // latency per gathered row; the element order of the sums is unchanged
+            float4 rv[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                if (lane + it * 32 < nvec) rv[it] = __ldg(rp + lane + it * 32);
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                if (lane + it * 32 < nvec) body(rv[it], s_q[lane + it * 32]);
+            for (int j = lane + 256; j < nvec; j += 32) body(__ldg(rp + j), s_q[j]);
         } else {
             // same element order as scan_f16_simt_kernel: 8 halfs per lane per step
             const uint4 *rp = (const uint4 *)rb;

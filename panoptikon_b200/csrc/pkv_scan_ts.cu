@@ -289,6 +289,13 @@ scan_i8_ts_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs 
             const int am_max = __reduce_max_sync(0xffffffffu, row_ok ? am : 0);
             nrow = a.row_begin + (tile + nseq) * TILE_N + col0 + lane;
             am = (tile + nseq < ntiles && nrow < a.row_end) ? __ldg(a.row_mag_i + nrow) : -1;
+            {
+                // the norms of the tile after next are pulled into L2 now (see pkv_scan_img8.cu: one slow DRAM access
+                // among the 32 epilogue warps of an accumulator stalls the whole hand-off)
+                const uint32_t prow = a.row_begin + (tile + 3 * nseq) * TILE_N + col0 + lane;
+                if (tile + 3 * nseq < ntiles && prow < a.row_end && (lane & 7) == 0)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.row_mag_i + prow));
+            }
             if (live) tq = prefilter_query_figure<METRIC>(*(volatile const float *)&sh->thr[qcol], bm_q);
             const int bound = prefilter_bound<METRIC>(tq, sqrtf((float)am_min), sqrtf((float)am_max), (float)am_min);
             tc::mbar_wait(&sh->tmem_full[buf], bph);

@@ -227,3 +227,52 @@ def test_guess_survives_sorted_insertion_order():
         got = ix.search(q, 50, pk.COSINE)
         assert ix.counters().fallback_queries == 0
     assert_close_topk(got, orc.topk(x, q, orc.COSINE, 50, threads=5), x, q, orc.COSINE)
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_exact_epilogue_culling_equals_flush_time_culling(metric):
+    """img8_epi = 1 (default): the epilogue bounds each surviving pair exactly in registers (row figures shuffled from
+    the lane that prefetched them) before it is held; 0: the same bound at flush time from the figures in global
+    memory.  Same filter, same exact keys: identical results, live and chunked."""
+    x, q = orc.synthetic(220_000, 320, 501), orc.synthetic(257, 320, 502)
+    x[1000:1010] *= 30.0          # rows whose figures differ from their neighbours' (the warp-wide bound is loose there)
+    x[5000] = np.nan
+    with _f32_index(x) as ix:
+        a = ix.search(q, 100, metric)
+        ix.set_option("img8_epi", 0)
+        b = ix.search(q, 100, metric)
+        ix.set_option("live", 0)
+        c = ix.search(q, 100, metric)
+        ix.set_option("img8_epi", 1)
+        d = ix.search(q, 100, metric)
+    assert _same(a, b) and _same(c, d) and _same(a, c)
+    assert_close_topk(a, orc.topk(x, q, metric, 100, threads=16), x, q, metric)
+
+
+def test_many_tight_guesses_fall_back_to_learnt_thresholds():
+    # rows close to each of 40 queries sit on the sample's stride: more failed guesses than the repair takes one by one
+    n, d, k = 150_001, 64, 100
+    x, q = orc.synthetic(n, d, 393), orc.synthetic(48, d, 394)
+    stride = n // 3968
+    rng = np.random.default_rng(40)
+    for i in range(40):
+        for j in range(50):
+            v = q[i] + rng.standard_normal(d).astype(np.float32) * 0.01
+            x[(i * 50 + j) * stride] = v / np.linalg.norm(v)
+    with _f32_index(x) as ix:
+        c0 = ix.counters()
+        got = ix.search(q, k, pk.COSINE)
+        assert ix.counters().fallback_queries > c0.fallback_queries
+    assert_close_topk(got, orc.topk(x, q, orc.COSINE, k, threads=8), x, q, orc.COSINE)
+
+
+def test_guess_rank_follows_the_corpus_size():
+    """The guessed start serves corpora from ~64k rows up; the repaired queries (if any) are counted, never wrong."""
+    for n, d, nq in ((70_000, 128, 64), (400_000, 128, 200)):
+        x, q = orc.synthetic(n, d, 511 + n % 7), orc.synthetic(nq, d, 512)
+        with _f32_index(x) as ix:
+            c0 = ix.counters()
+            got = ix.search(q, 100, pk.COSINE)
+            c1 = ix.counters()
+            assert c1.kernel_launches - c0.kernel_launches <= 8 or c1.fallback_queries > c0.fallback_queries
+        assert_close_topk(got, orc.topk(x, q, orc.COSINE, 100, threads=16), x, q, orc.COSINE)

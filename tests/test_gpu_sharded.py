@@ -15,7 +15,7 @@ def _same(a, b):
             and np.array_equal(a[2], b[2]))
 
 
-@pytest.mark.parametrize("shards", [2, 3, 5])
+@pytest.mark.parametrize("shards", [2, 3, 5, 8])
 def test_single_process_shards_equal_one_index_f32(shards):
     n, d = 70_001, 256
     x, q = orc.synthetic(n, d, 401), orc.synthetic(70, d, 402)
@@ -83,3 +83,24 @@ def test_nccl_communicator_single_rank_round_trip():
     finally:
         comm.close()
     assert _same(got, one)
+
+
+def test_single_process_shards_over_every_visible_gpu():
+    """The 8-shard layout of BASELINE configs 4/5 with one shard per device when the box has several (the driver's
+    single-GPU box runs it as 8 shards on device 0: same library path, same merge order)."""
+    import torch
+
+    ndev = torch.cuda.device_count()
+    devices = [i % ndev for i in range(8)]
+    n, d = 400_000, 128
+    x, q = orc.synthetic(n, d, 441), orc.synthetic(64, d, 442)
+    rng = np.random.default_rng(44)
+    bm = np.packbits(rng.random(((n + 63) // 64) * 64) < 0.1, bitorder="little").view(np.uint64)
+    with pk.ShardedIndex(d, pk.F32, devices=devices, total_rows=n) as sx:
+        sx.append(x)
+        sx.seal()
+        assert len(sx.shard_rows()) == 8 and sum(sx.shard_rows()) == n
+        got = sx.search(q, 100, pk.COSINE)
+        got_bm = sx.search(q, 100, pk.COSINE, bitmap=bm)      # config 5: one global tag bitmap, sliced per shard
+    assert_close_topk(got, orc.topk(x, q, orc.COSINE, 100, threads=16), x, q, orc.COSINE)
+    assert_close_topk(got_bm, orc.topk(x, q, orc.COSINE, 100, bitmap=bm, threads=16), x, q, orc.COSINE)
