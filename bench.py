@@ -804,6 +804,8 @@ def main():
             "gpu_launches": int(timed["c1"].kernel_launches - timed["c0"].kernel_launches) + timed["merge_launches"],
             "roofline": roof,
             "sustained": sustained,
+            # queries searched a second time: candidate-list overflows (whole batch redone) + guessed thresholds that proved
+            # too tight (that query alone redone)
             "overflow_rescans": int(timed["c1"].fallback_queries - timed["c0"].fallback_queries),
             # what the in-kernel machinery did per step (device counters of the searches in the timed region)
             "search_stats": w.search_stats(timed),

@@ -349,7 +349,13 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     const int64_t live_start = ix.opt.live_start_rows > 0 ? ix.opt.live_start_rows : 131072;
     // Measured on B200 (profiles/README.md, round 2): the live launch has a start-up transient and a drain tail that
     // only a long enough scan amortises; below ~0.7M rows the chunked schedule with deferred band pairs is faster.
-    if (ix.opt.live == 1 && N - live_start < ix.opt.live_min_rows) r.live_capable = false;
+    // (A guessed start has no prefix to amortise: measured faster than the chunked schedule from 100k rows up -
+    // 100k / 250k / 500k rows: 406 k / 306 k / 249 k queries/s against 355 k / 259 k / 240 k - so it lifts this limit.)
+    static const bool trace_env = getenv("PKV_TRACE") != nullptr;
+    const bool guess_possible = allow_guess && ix.opt.guess && ix.opt.optimistic && !d_bitmap && !trace_env &&
+                                ix.sample_rows > 0 && ix.sample_of_rows == N && N <= ix.opt.guess_max_rows &&
+                                ix.sample_rows <= r.safe_rows && ix.opt.live_start_rows == 0;
+    if (ix.opt.live == 1 && N - live_start < ix.opt.live_min_rows && !guess_possible) r.live_capable = false;
     ScanArgs &a = r.args;
     a.data = ix.d_data;
     a.pitch_bytes = ix.pitch;
@@ -402,7 +408,6 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // is checked once at the end and, if it ever fired, the search is redone with a sync per chunk
     // (which is what splits overflowing ranges).  Bitmap searches stay careful until every query has a
     // threshold: their candidate rate is unknown until the first members are seen.
-    static const bool trace_env = getenv("PKV_TRACE") != nullptr;
     const int kind_code =
         r.use_tc_f32 ? scan_tc_f32_kind(ix, nq) : r.use_tc ? 3 : (ix.dtype == PKV_F32 ? 1 : (ix.dtype == PKV_I8 ? 2 : 5));
     bool optimistic = ix.opt.optimistic && !d_bitmap && !trace_env;
@@ -418,8 +423,7 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // 16: 215 k / 193 k / 167 k / 147 k queries/s; 10M rows r = 5 / 10: 78 k / 73 k (chunked prefix: 74 k), r = 20
     // overflows the candidate lists (the burst before the thresholds tighten) - hence the cap on the admitted rows.
     int guess_rank = 0;
-    if (allow_guess && allow_live && ix.opt.guess && optimistic && ix.sample_rows > 0 && ix.sample_of_rows == N &&
-        N <= ix.opt.guess_max_rows && ix.sample_rows <= r.safe_rows && ix.opt.live_start_rows == 0) {
+    if (guess_possible && allow_live && optimistic) {
         const double x = (double)k * (double)ix.sample_rows / (double)N;
         int rank;
         if (ix.opt.guess_factor > 0) {   // explicit tightness (experiments): this many times k rows beat the guess

@@ -64,6 +64,7 @@ struct ImgArgs {
                              // filter's error band (and, fused, whatever the ring cannot take) are parked with their dot
                              // product and re-checked against the FINAL thresholds at the end of the search
     int rows_f16;            // stored rows are fp16 (f16 index), else f32
+    unsigned long long *dbg; // PKV_TILE_TIMING builds only: per-warp clock sums of the accumulator hand-off (tools/gpu/tile_timing.py)
     int park_lean;           // parked pairs carry (row, dot) only: the deferred pass reads the row figures itself
     int epi_exact;           // the epilogue culls with the EXACT per-pair bound in registers (row figures shuffled from the
                              // lane that prefetched them) before a pair enters the hold list: the flush has no
@@ -742,14 +743,31 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             constexpr uint32_t idesc = tc::make_idesc(/*S32*/ 2, /*INT8*/ 1, NCTA * QM_CTA, TILE_N);
             const bool issuer = tc::elect_one();
             uint32_t s = 0, ph = 0, buf = 0, bph = 0;
+#ifdef PKV_TILE_TIMING
+            long long tt_empty = 0, tt_full = 0, tt_issue = 0, tt_n = 0;
+#endif
             for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
+#ifdef PKV_TILE_TIMING
+                const long long tt0 = clock64();
+#endif
                 tc::mbar_wait(&sh->tmem_empty[buf], bph ^ 1);
                 tc::fence_after_sync();
+#ifdef PKV_TILE_TIMING
+                const long long tt1 = clock64();
+                tt_empty += tt1 - tt0;
+                ++tt_n;
+#endif
                 const uint32_t d_tmem = tmem_base + acc_col0 + buf * TILE_N;
                 for (int kc = 0; kc < kchunks; kc += CPS) {
                     const int n = kchunks - kc < CPS ? kchunks - kc : CPS;
+#ifdef PKV_TILE_TIMING
+                    const long long tf0 = clock64();
+#endif
                     tc::mbar_wait(&sh->full[s], ph);
                     tc::fence_after_sync();
+#ifdef PKV_TILE_TIMING
+                    tt_full += clock64() - tf0;
+#endif
                     const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(s_b) + s * STAGE_BYTES);
                     const uint32_t a_tmem = tmem_base + (uint32_t)kc * (CHUNK_BYTES / 4);
                     if (issuer) {
@@ -777,7 +795,17 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                 }
                 __syncwarp();
                 if (++buf == NBUF) { buf = 0; bph ^= 1; }
+#ifdef PKV_TILE_TIMING
+                tt_issue += clock64() - tt1;
+#endif
             }
+#ifdef PKV_TILE_TIMING
+            if (im.dbg && lane == 0) {
+                unsigned long long *o = im.dbg + ((size_t)blockIdx.x * 20 + warp) * 8;
+                o[0] = (unsigned long long)tt_n; o[1] = (unsigned long long)tt_empty; o[2] = (unsigned long long)tt_full;
+                o[3] = (unsigned long long)tt_issue;
+            }
+#endif
         }
     } else if (seq < nseq && warp - 2 < EPI_USED) {
         // ===================== epilogue: own 128 queries x the tile's rows =====================
@@ -800,6 +828,10 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         float4 qc;
         float qs;
         query_consts<METRIC>(qm, thr0, qc, qs);
+#ifdef PKV_TILE_TIMING
+        long long te_wait = 0, te_ld = 0, te_proc = 0, te_n = 0, te_max = 0, te_slow = 0, te_pre = 0;
+        long long te_prev = clock64();
+#endif
         for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
             if (live) query_consts<METRIC>(qm, *(volatile const float *)&sh->thr[qcol], qc, qs);
@@ -827,8 +859,21 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             float bf = pair_bound<METRIC>(qc, qs, x1lo, x1hi, x2lo, x2hi, vhi, whi, uhi);
             bf = fminf(fmaxf(bf, -BOUND_CLAMP), BOUND_CLAMP);  // NaN -> -clamp: keep everything
             const int bound = real_q ? __float2int_rd(bf) : (int)BOUND_CLAMP;
+#ifdef PKV_TILE_TIMING
+            const long long ta = clock64();   // bound of this tile computed: (ta - te_prev) = processing of the previous tile + this bound
+            {
+                const long long p = ta - te_prev;
+                te_proc += p;
+                if (p > te_max) te_max = p;
+                if (p > 1500) ++te_slow;
+            }
+#endif
             tc::mbar_wait(&sh->tmem_full[buf], bph);
             tc::fence_after_sync();
+#ifdef PKV_TILE_TIMING
+            const long long tb = clock64();
+            te_wait += tb - ta;
+#endif
             uint32_t v[32];
             tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col0 + buf * TILE_N + col0, v);
             tc::tmem_ld_wait();
@@ -838,6 +883,11 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                 if (PAIR) tc::mbar_arrive_cluster(empty0 + buf * 8u);  // accumulator is in registers
                 else tc::mbar_arrive(&sh->tmem_empty[buf]);
             }
+#ifdef PKV_TILE_TIMING
+            te_prev = clock64();
+            te_ld += te_prev - tb;
+            ++te_n;
+#endif
             if (++buf == NBUF) { buf = 0; bph ^= 1; }
             if (!im.epi_exact) {
                 // round 1: sign bit of (bound - 1 - d) is set iff d >= bound: OR them all, branch once per lane
@@ -915,19 +965,11 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                         }
                     }
                 } else {
-                    // three or more rows of one query in one 32-row slice: survivors are DENSE (a chunk scanned with
-                    // a threshold learnt from few rows) - the round-1 list, filled through its shared-memory counter and
-                    // emptied lane-parallel right away, is the cheaper tool there
-                    if (hold_n) {
-                        pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
-                        hold_n = 0;
-                    }
+                    // three or more rows of one query in one 32-row slice (rare in a live launch, whose thresholds are
+                    // tight; the dense chunks of a learning prefix run the round-1 epilogue): pair by pair
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int d = (int)v[j];
-                        if (d >= bound) hold_img<METRIC>(a, im, qbase, qcol, d, row_first + j, sh, ew);
-                    }
-                    flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
+                    for (int j = 0; j < 32; ++j)
+                        if ((int)v[j] >= bound) consider_img<METRIC>(a, im, qbase, (uint32_t)qcol, (int)v[j], row_first + j, sh);
                 }
             }
             if (hold_n >= (uint32_t)HOLD_FLUSH) {
@@ -941,6 +983,14 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         } else {
             flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
         }
+#ifdef PKV_TILE_TIMING
+        if (im.dbg && lane == 0) {
+            unsigned long long *o = im.dbg + ((size_t)blockIdx.x * 20 + warp) * 8;
+            o[0] = (unsigned long long)te_n; o[1] = (unsigned long long)te_wait; o[2] = (unsigned long long)te_ld;
+            o[3] = (unsigned long long)te_proc; o[4] = (unsigned long long)te_max; o[5] = (unsigned long long)te_slow;
+        }
+        (void)te_pre;
+#endif
         __syncwarp();
         if (lane == 0) {  // this warp has published its last survivor
             __threadfence_block();
@@ -1336,7 +1386,11 @@ static ImgArgs img_args(const Index &ix, const ScanArgs &a, Workspace &ws) {
     im.fused = (ix.opt.img8_fused >= 2 || a.topk.live) ? 1 : 0;
     im.defer = a.topk.defer;
     im.rows_f16 = ix.dtype == PKV_F16 ? 1 : 0;
-    im.epi_exact = ix.opt.img8_epi;
+    // the round-2 epilogue serves live launches (tight thresholds, rare survivors); the chunks of a learning prefix pass
+    // several rows per query and 32-row slice, which the round-1 hold lists handle better (measured: 500k rows chunked
+    // 240 k queries/s with the round-1 epilogue, 183 k with the round-2 one)
+    im.dbg = nullptr;
+    im.epi_exact = (ix.opt.img8_epi && a.topk.live) ? 1 : 0;
     im.park_lean = ix.opt.img8_epi ? 1 : 0;
     if (im.park_lean) im.dlist.meta = nullptr;
     return im;
@@ -1383,6 +1437,15 @@ int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStre
         ws.q8_ready = true;
     }
     const int kchunks = ix.dim_pad8 / CHUNK_BYTES;
+#ifdef PKV_TILE_TIMING
+    static unsigned long long *d_dbg = nullptr;
+    const size_t dbg_n = (size_t)256 * 20 * 8;
+    if (!d_dbg) cudaMalloc((void **)&d_dbg, dbg_n * 8);
+    if (a.topk.live) {
+        cudaMemsetAsync(d_dbg, 0, dbg_n * 8, s);
+        im.dbg = d_dbg;
+    }
+#endif
     switch (a.metric) {
         case PKV_COSINE: PKV_TRY(launch_img8_metric<PKV_COSINE>(ix, a, im, kchunks, s, launches)); break;
         case PKV_L2: PKV_TRY(launch_img8_metric<PKV_L2>(ix, a, im, kchunks, s, launches)); break;
