@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpkv.so")
+LIB_PATH = os.environ.get("PKV_LIB_PATH") or os.path.join(HERE, "libpkv.so")   # (PKV_LIB_PATH: instrumented debug builds)
 
 OK, ERR_INVALID, ERR_DIM_MISMATCH, ERR_NOT_READY, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = range(7)
 F32, I8, F16 = 0, 1, 2

@@ -181,10 +181,52 @@ __device__ __forceinline__ bool ring_try_push(ImgShared *sh, uint32_t row, uint3
     }
 }
 
+constexpr uint32_t COL_CHECKED = 0x80000000u, COL_LIKELY = 0x40000000u;
+#ifndef RING_PUBLISH_FENCE
+#define RING_PUBLISH_FENCE() __threadfence_block()
+#endif
+// Warp-cooperative, non-blocking push of up to 32 survivors (one per lane in `want`) into the CTA's ring: ONE
+// compare-and-swap reserves consecutive tickets for as many of them as have a free slot ahead (lane-serial pushes cost
+// one shared-memory CAS round trip each - measured 10 000 clocks per 32-entry flush, with the accumulator hand-off of
+// the whole CTA pair waiting behind it).  Returns the lanes that did not get in (ring full): they are parked.
+__device__ __forceinline__ unsigned ring_push_warp(ImgShared *sh, unsigned want, int lane, uint32_t row, uint32_t col, int d) {
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int attempt = 0; attempt < 16 && want; ++attempt) {
+        uint32_t t = 0;
+        const int leader = __ffs(want) - 1;
+        if (lane == leader) t = *(volatile uint32_t *)&sh->ring_head;
+        t = __shfl_sync(0xffffffffu, t, leader);
+        const bool mine = (want >> lane) & 1u;
+        const uint32_t rank = (uint32_t)__popc(want & lt);
+        const uint32_t ticket = t + rank, i = ticket & RING_MASK;
+        // the slot's previous entry must have been read (tickets are handed out in order, slots are freed in any order)
+        const bool busy = mine && *(volatile uint32_t *)&sh->ring_seq[i] != ticket;
+        const unsigned blocked = __ballot_sync(0xffffffffu, busy);
+        // lanes ranked below the first blocked one get in
+        const uint32_t m = blocked ? (uint32_t)__popc(want & ((1u << (__ffs(blocked) - 1)) - 1u)) : (uint32_t)__popc(want);
+        if (m == 0) break;  // full
+        uint32_t ok = 0;
+        if (lane == leader) ok = atomicCAS(&sh->ring_head, t, t + m) == t ? 1u : 0u;
+        ok = __shfl_sync(0xffffffffu, ok, leader);
+        if (!ok) continue;  // another warp moved the head: look again
+        const bool in = mine && rank < m;
+        if (in) {
+            sh->ring_row[i] = row;
+            sh->ring_dot[i] = d;
+            sh->ring_col[i] = (uint16_t)col;
+            RING_PUBLISH_FENCE();
+            *(volatile uint32_t *)&sh->ring_seq[i] = ticket + 1u;
+        }
+        want &= ~__ballot_sync(0xffffffffu, in);
+        if (blocked) break;  // the ring is full behind what just got in
+    }
+    return want;
+}
+
+
 // One pre-filter survivor: exact per-pair bound, membership, then hand the row on for exact re-scoring.
 // `col` bit 31 set: the pair already passed the per-pair bound in the epilogue's registers (epi_exact) and bit 30 says
 // whether it is a LIKELY candidate; nothing is left to check but membership.
-constexpr uint32_t COL_CHECKED = 0x80000000u, COL_LIKELY = 0x40000000u;
 template <int METRIC>
 __device__ __noinline__ void consider_img(const ScanArgs &a, const ImgArgs &im, int qbase, uint32_t colw, int d, uint32_t row,
                                           ImgShared *sh) {
@@ -542,11 +584,12 @@ __device__ __forceinline__ void flush_img(const ScanArgs &a, const ImgArgs &im, 
     __syncwarp();
 }
 
-// img8_epi = 1 (round 2): the list is filled warp-uniformly (ballot + prefix popcount, the fill count is a register)
-// with pairs that already passed the exact per-pair bound in registers; the flush has no dependent global load left.
-// A pair that must be PARKED (outside the in-kernel re-scorer's reach) only ISSUES the atomic that reserves its slot in
-// the query's parked list; the three stores that need the slot are made at the next flush (or at the end of the scan),
-// when the atomic has long returned: the epilogue warp never waits for a global round trip between two accumulators.
+// img8_epi = 1 (round 2, live launches): the list is filled warp-uniformly (ballot + prefix popcount, the fill count is
+// a register) with pairs that already passed the exact per-pair bound in registers; the flush has no dependent global
+// load left.  A pair that must be PARKED (outside the in-kernel re-scorer's reach) only ISSUES the atomic that reserves
+// its slot in the query's parked list; the two stores that need the slot are made at the next flush (or at the end of the
+// scan), when the atomic has long returned: the epilogue warp never waits for a global round trip between two
+// accumulators.
 struct ParkPending {
     uint32_t slot, row;
     int d, q;  // q < 0: nothing pending
@@ -562,32 +605,43 @@ __device__ __forceinline__ void park_complete(const ImgArgs &im, ParkPending &pp
     }
 }
 
+// One round (<= 32 entries from `base`) of a hold-list flush: membership, the ring for the likely candidates; what must
+// be PARKED comes back to the caller in registers - the caller issues the atomic that reserves the slot INLINE, so that
+// its result can stay pending across the tile loop (a function must wait for its outstanding loads before it returns:
+// measured 10 000 clocks per flush while the atomic was issued in here).
+struct HeldOut {
+    uint32_t row;
+    int d, q;  // q < 0: nothing to park
+};
+
 template <int METRIC>
-__device__ __noinline__ ParkPending flush_held(const ScanArgs &a, const ImgArgs &im, int qbase, ImgShared *sh, int ew, int lane,
-                                               uint32_t n, ParkPending pp) {
-    __syncwarp();
-    for (uint32_t base = 0; base < n; base += 32) {
-        park_complete(im, pp);  // (a second round of one flush waits for the first round's atomics: n > 32 is rare)
-        const uint32_t e = base + (uint32_t)lane;
-        if (e < n) {
-            const uint32_t colw = sh->hold_col[ew][e], row = sh->hold_row[ew][e];
-            const int d = sh->hold_dot[ew][e];
-            const int col = (int)(colw & 0xffffu), q = qbase + col;
-            const bool parkable = (colw & COL_CHECKED) && im.fused && im.defer && im.park_lean;
-            if (!parkable) {
-                consider_img<METRIC>(a, im, qbase, colw, d, row, sh);  // every other mode: the synchronous path
-            } else if (q < a.nq && row < a.row_end && topk_member(a.topk, q, row)) {
-                if (!((colw & COL_LIKELY) && ring_try_push(sh, row, (uint32_t)col, d))) {
-                    pp.slot = atomicAdd(im.dlist.cnt + q, 1u);  // issued now, consumed at the next flush
-                    pp.row = row;
-                    pp.d = d;
-                    pp.q = q;
-                }
-            }
+__device__ __noinline__ HeldOut flush_round(const ScanArgs &a, const ImgArgs &im, int qbase, ImgShared *sh, int ew, int lane,
+                                            uint32_t base, uint32_t n) {
+    const uint32_t e = base + (uint32_t)lane;
+    HeldOut out{0u, 0, -1};
+    uint32_t colw = 0;
+    bool park = false, likely = false;
+    if (e < n) {
+        colw = sh->hold_col[ew][e];
+        out.row = sh->hold_row[ew][e];
+        out.d = sh->hold_dot[ew][e];
+        const int col = (int)(colw & 0xffffu);
+        const bool parkable = (colw & COL_CHECKED) && im.fused && im.defer && im.park_lean;
+        if (!parkable) {
+            consider_img<METRIC>(a, im, qbase, colw, out.d, out.row, sh);  // every other mode: the synchronous path
+        } else if (qbase + col < a.nq && out.row < a.row_end && topk_member(a.topk, qbase + col, out.row)) {
+            out.q = qbase + col;
+            park = true;
+            likely = (colw & COL_LIKELY) != 0;
         }
     }
-    __syncwarp();
-    return pp;
+    // the likely candidates go to the in-kernel re-scorer if the ring has room; everything else is parked
+    const unsigned want = __ballot_sync(0xffffffffu, park && likely);
+    if (want) {
+        const unsigned left = ring_push_warp(sh, want, lane, out.row, colw & 0xffffu, out.d);
+        if (((want & ~left) >> lane) & 1u) out.q = -1;
+    }
+    return out;
 }
 
 // non-negative floats order like their bit patterns: hardware warp min/max on the unsigned view
@@ -816,6 +870,43 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         uint32_t buf = 0, bph = 0;
         uint32_t hold_n = 0;  // entries in this warp's hold list (warp-uniform; img8_epi = 1)
         ParkPending pp{0u, 0u, 0, -1};
+        // Flushes the first 32 held entries (one lane-parallel round: a second round would have to wait for the atomics
+        // the first one has just issued) and moves the rest to the front of the list; `all`: the end of the scan.
+        auto flush_held = [&](bool all) {
+            __syncwarp();
+            for (uint32_t base = 0; base < hold_n; base += 32) {
+                const HeldOut h = flush_round<METRIC>(a, im, qbase, sh, ew, lane, base, hold_n < base + 32 ? hold_n : base + 32);
+                park_complete(im, pp);
+                if (h.q >= 0) {
+                    pp.slot = atomicAdd(im.dlist.cnt + h.q, 1u);  // issued now, consumed at the next flush
+                    pp.row = h.row;
+                    pp.d = h.d;
+                    pp.q = h.q;
+                }
+                if (!all) break;
+            }
+            __syncwarp();
+            if (!all && hold_n > 32) {
+                const uint32_t rest = hold_n - 32;
+                uint32_t r0 = 0, r2 = 0;
+                int r1 = 0;
+                if ((uint32_t)lane < rest) {
+                    r0 = sh->hold_row[ew][32 + lane];
+                    r1 = sh->hold_dot[ew][32 + lane];
+                    r2 = sh->hold_col[ew][32 + lane];
+                }
+                __syncwarp();
+                if ((uint32_t)lane < rest) {
+                    sh->hold_row[ew][lane] = r0;
+                    sh->hold_dot[ew][lane] = r1;
+                    sh->hold_col[ew][lane] = r2;
+                }
+                __syncwarp();
+                hold_n = rest;
+            } else {
+                hold_n = 0;
+            }
+        };
         const uint32_t lt_mask = (1u << lane) - 1u;
         // lane j prefetches the figures of row col0 + j (the warp's 32 rows of the tile)
         uint32_t nrow = a.row_begin + seq * TILE_N + col0 + lane;
@@ -829,10 +920,14 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         float qs;
         query_consts<METRIC>(qm, thr0, qc, qs);
 #ifdef PKV_TILE_TIMING
-        long long te_wait = 0, te_ld = 0, te_proc = 0, te_n = 0, te_max = 0, te_slow = 0, te_pre = 0;
+        long long te_wait = 0, te_ld = 0, te_proc = 0, te_n = 0, te_max = 0, te_slow = 0, te_pre = 0, te_pre_slow = 0, te_flush = 0, te_nflush = 0, te_fmax = 0;
+        long long tf_round = 0, tf_park = 0, tf_atom = 0;
         long long te_prev = clock64();
 #endif
         for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
+#ifdef PKV_TILE_TIMING
+            const long long t_top = clock64();
+#endif
             const uint32_t row_first = a.row_begin + tile * TILE_N + col0;
             if (live) query_consts<METRIC>(qm, *(volatile const float *)&sh->thr[qcol], qc, qs);
             // loosest figures over the warp's 32 rows (rows past the end must not loosen them)
@@ -861,6 +956,8 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             const int bound = real_q ? __float2int_rd(bf) : (int)BOUND_CLAMP;
 #ifdef PKV_TILE_TIMING
             const long long ta = clock64();   // bound of this tile computed: (ta - te_prev) = processing of the previous tile + this bound
+            te_pre += ta - t_top;
+            if (ta - t_top > 1500) ++te_pre_slow;
             {
                 const long long p = ta - te_prev;
                 te_proc += p;
@@ -904,31 +1001,47 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                 flush_img<METRIC>(a, im, qbase, sh, ew, lane, HOLD_FLUSH);
                 continue;
             }
-            // round 2.  The largest of the lane's 32 dot products against the bound (3-input max: 16 instructions), one
-            // branch for the whole warp
-            int vmax = (int)v[0];
+            // round 2.  The largest of the lane's 32 dot products against the bound: maxima of 8 groups of 4 rows first
+            // (3-input max: 20 instructions in all), one branch for the whole warp
+            int g[8];
 #pragma unroll
-            for (int j = 1; j < 31; j += 2) vmax = __vimax3_s32(vmax, (int)v[j], (int)v[j + 1]);
-            vmax = max(vmax, (int)v[31]);
+            for (int i = 0; i < 8; ++i)
+                g[i] = max(__vimax3_s32((int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2]), (int)v[4 * i + 3]);
+            const int vmax = __vimax3_s32(__vimax3_s32(g[0], g[1], g[2]), __vimax3_s32(g[3], g[4], g[5]), max(g[6], g[7]));
             if (__any_sync(0xffffffffu, vmax >= bound)) {
-                // straight-line, predicated: each lane (query) notes how many of its 32 rows pass and which was the last
+                // which groups hold a survivor of ANY lane (one warp-wide OR): only those are looked at row by row -
+                // straight-line, predicated: each lane (query) notes how many of its rows pass and which was the last
+                uint32_t gm = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gm |= g[i] >= bound ? (1u << i) : 0u;
+                const uint32_t gw = __reduce_or_sync(0xffffffffu, gm);
                 int n = 0, ej = 0, ed = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if ((int)v[j] >= bound) {
-                        ej = j;
-                        ed = (int)v[j];
-                        ++n;
+                for (int i = 0; i < 8; ++i) {
+                    if (gw & (1u << i)) {
+#pragma unroll
+                        for (int j = 4 * i; j < 4 * i + 4; ++j) {
+                            if ((int)v[j] >= bound) {
+                                ej = j;
+                                ed = (int)v[j];
+                                ++n;
+                            }
+                        }
                     }
                 }
                 int fj = ej, fd = ed;
                 const int nmax = __reduce_max_sync(0xffffffffu, n);
-                if (nmax >= 2) {  // some lane has two: the FIRST of each lane as well
+                if (nmax == 2) {  // some lane has two: the FIRST of each lane as well
 #pragma unroll
-                    for (int j = 31; j >= 0; --j) {
-                        if ((int)v[j] >= bound) {
-                            fj = j;
-                            fd = (int)v[j];
+                    for (int i = 7; i >= 0; --i) {
+                        if (gw & (1u << i)) {
+#pragma unroll
+                            for (int j = 4 * i + 3; j >= 4 * i; --j) {
+                                if ((int)v[j] >= bound) {
+                                    fj = j;
+                                    fd = (int)v[j];
+                                }
+                            }
                         }
                     }
                 }
@@ -959,10 +1072,7 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                             sh->hold_col[ew][slot] = colw;
                         }
                         hold_n += (uint32_t)__popc(mask);
-                        if (hold_n > (uint32_t)(HOLD_CAP - 32)) {  // the next round may add 32 more
-                            pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
-                            hold_n = 0;
-                        }
+                        if (hold_n > (uint32_t)(HOLD_CAP - 32)) flush_held(false);  // the next round may add 32 more
                     }
                 } else {
                     // three or more rows of one query in one 32-row slice (rare in a live launch, whose thresholds are
@@ -972,13 +1082,10 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
                         if ((int)v[j] >= bound) consider_img<METRIC>(a, im, qbase, (uint32_t)qcol, (int)v[j], row_first + j, sh);
                 }
             }
-            if (hold_n >= (uint32_t)HOLD_FLUSH) {
-                pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
-                hold_n = 0;
-            }
+            if (hold_n >= (uint32_t)HOLD_FLUSH) flush_held(false);
         }
         if (im.epi_exact) {
-            if (hold_n) pp = flush_held<METRIC>(a, im, qbase, sh, ew, lane, hold_n, pp);
+            if (hold_n) flush_held(true);
             park_complete(im, pp);
         } else {
             flush_img<METRIC>(a, im, qbase, sh, ew, lane, 1);
@@ -988,8 +1095,13 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
             unsigned long long *o = im.dbg + ((size_t)blockIdx.x * 20 + warp) * 8;
             o[0] = (unsigned long long)te_n; o[1] = (unsigned long long)te_wait; o[2] = (unsigned long long)te_ld;
             o[3] = (unsigned long long)te_proc; o[4] = (unsigned long long)te_max; o[5] = (unsigned long long)te_slow;
+            o[6] = (unsigned long long)te_pre; o[7] = (unsigned long long)te_pre_slow;
+            unsigned long long *o2 = im.dbg + (size_t)256 * 20 * 8 + ((size_t)blockIdx.x * 20 + warp) * 4;
+            o2[0] = (unsigned long long)te_flush; o2[1] = (unsigned long long)te_nflush; o2[2] = (unsigned long long)te_fmax;
+            o2[3] = (unsigned long long)tf_round;
+            unsigned long long *o3 = im.dbg + (size_t)256 * 20 * 12 + ((size_t)blockIdx.x * 20 + warp) * 2;
+            o3[0] = (unsigned long long)tf_park; o3[1] = (unsigned long long)tf_atom;
         }
-        (void)te_pre;
 #endif
         __syncwarp();
         if (lane == 0) {  // this warp has published its last survivor
@@ -1425,6 +1537,19 @@ int launch_rescore_deferred(const Index &ix, const ScanArgs &a, Workspace &ws, c
     return PKV_OK;
 }
 
+#ifdef PKV_TILE_TIMING
+static unsigned long long *g_tile_timing = nullptr;
+}  // namespace pkv
+// debug builds only (tools/gpu/tile_timing.py): the per-warp clock sums of the last live launch
+extern "C" int pkv_debug_tile_timing(unsigned long long *out, size_t n) {
+    if (!pkv::g_tile_timing) return -1;
+    cudaDeviceSynchronize();
+    const size_t have = (size_t)256 * 20 * 14;
+    return (int)cudaMemcpy(out, pkv::g_tile_timing, (n < have ? n : have) * 8, cudaMemcpyDeviceToHost);
+}
+namespace pkv {
+#endif
+
 int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStream_t s, int *launches) {
     if (a.row_end <= a.row_begin || a.nq <= 0) return PKV_OK;
     ImgArgs im = img_args(ix, a, ws);
@@ -1438,8 +1563,8 @@ int launch_scan_img8(const Index &ix, const ScanArgs &a, Workspace &ws, cudaStre
     }
     const int kchunks = ix.dim_pad8 / CHUNK_BYTES;
 #ifdef PKV_TILE_TIMING
-    static unsigned long long *d_dbg = nullptr;
-    const size_t dbg_n = (size_t)256 * 20 * 8;
+    unsigned long long *&d_dbg = g_tile_timing;
+    const size_t dbg_n = (size_t)256 * 20 * 14;
     if (!d_dbg) cudaMalloc((void **)&d_dbg, dbg_n * 8);
     if (a.topk.live) {
         cudaMemsetAsync(d_dbg, 0, dbg_n * 8, s);
