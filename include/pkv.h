@@ -345,6 +345,11 @@ int pkv_index_counters(pkv_index *h, pkv_counters *out);
  * compare them; those are listed in INTEGRATION.md section 4 and are not part of the supported surface.  Unknown names
  * are PKV_ERR_INVALID. */
 int pkv_index_set_option(pkv_index *h, const char *name, int64_t value);
+/* The sample rank a guessed start uses: with x = k * sample_rows / rows sample rows expected among
+ * the corpus' true top-k, the smallest rank r >= 2 with P[Poisson(x) >= r] <= miss_ppm * 1e-6 - the r-th best sample
+ * distance is then too tight a threshold for a query with at most that probability; 0 when a guess would admit more rows
+ * than the candidate lists survive (the search then learns its thresholds on a chunked prefix).  Pure host arithmetic. */
+int pkv_guess_rank(int k, int64_t sample_rows, int64_t rows, int miss_ppm);
 
 /* -- PQL operator policy: pql/preprocess.rs:314-465, builder/filters/embedding_types.rs --- */
 typedef enum { PKV_INDEX_AUTO = 0, PKV_INDEX_EXACT = 1, PKV_INDEX_QUANT = 2, PKV_INDEX_ANN = 3 } pkv_index_mode;

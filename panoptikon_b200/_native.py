@@ -86,6 +86,7 @@ SIGNATURES = {
     "pkv_last_error": (C.c_char_p, []),
     "pkv_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pkv_scale_from_absmax": (C.c_float, [C.c_float]),
+    "pkv_guess_rank": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int]),
     "pkv_scale_artifact": (None, [C.c_float, _P]),
     "pkv_artifact_scale": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_float)]),
     "pkv_blob_absmax": (C.c_int, [C.c_int, _P, C.c_int64, C.POINTER(C.c_float)]),

@@ -424,22 +424,15 @@ static int search_batch(Index &ix, Workspace &ws, cudaStream_t s, const void *d_
     // overflows the candidate lists (the burst before the thresholds tighten) - hence the cap on the admitted rows.
     int guess_rank = 0;
     if (guess_possible && allow_live && optimistic) {
-        const double x = (double)k * (double)ix.sample_rows / (double)N;
         int rank;
         if (ix.opt.guess_factor > 0) {   // explicit tightness (experiments): this many times k rows beat the guess
-            rank = (int)((double)ix.opt.guess_factor * x + 0.5);
+            rank = (int)((double)ix.opt.guess_factor * (double)k * (double)ix.sample_rows / (double)N + 0.5);
+            const double admitted = (double)rank * (double)N / (double)ix.sample_rows;
+            if (rank < 2 || rank > ix.sample_rows / 4 || admitted > 16000.0) rank = 0;
         } else {
-            const double eps = (double)ix.opt.guess_miss_ppm * 1e-6;
-            double term = exp(-x), cdf = 0.0;
-            for (rank = 0; rank < 4096; ++rank) {
-                if (rank >= 2 && 1.0 - cdf <= eps) break;
-                cdf += term;
-                term *= x / (double)(rank + 1);
-            }
+            rank = pkv_guess_rank(k, ix.sample_rows, N, ix.opt.guess_miss_ppm);
         }
-        // the lists must survive the burst of rows a guess admits before the in-kernel feedback tightens it
-        const double admitted = (double)rank * (double)N / (double)ix.sample_rows;
-        if (rank >= 2 && rank <= ix.sample_rows / 4 && admitted <= 16000.0) guess_rank = rank;
+        guess_rank = rank;
     }
 restart:
     int64_t pos = 0;
@@ -1382,6 +1375,23 @@ int pkv_index_counters(pkv_index *h, pkv_counters *out) {
     out->last_total_ms = g_last.total_ms;
     out->last_scan_kind = g_last.kind;
     return PKV_OK;
+}
+
+int pkv_guess_rank(int k, int64_t sample_rows, int64_t rows, int miss_ppm) {
+    if (k < 1 || sample_rows < 1 || rows < 1) return 0;
+    const double x = (double)k * (double)sample_rows / (double)rows;
+    const double eps = (double)miss_ppm * 1e-6;
+    double term = exp(-x), cdf = 0.0;  // term = P[Poisson(x) = rank], cdf = P[Poisson(x) < rank]
+    int rank;
+    for (rank = 0; rank < 4096; ++rank) {
+        if (rank >= 2 && 1.0 - cdf <= eps) break;
+        cdf += term;
+        term *= x / (double)(rank + 1);
+    }
+    // the lists must survive the burst of rows a guess admits before the in-kernel feedback tightens it
+    const double admitted = (double)rank * (double)rows / (double)sample_rows;
+    if (rank > sample_rows / 4 || admitted > 16000.0) return 0;
+    return rank;
 }
 
 int pkv_index_set_option(pkv_index *h, const char *name, int64_t value) {

@@ -157,3 +157,24 @@ def test_cross_modal_host_policy():
     assert pk.resolve_ready_pair([a, "not-ready"]) is None                        # an existing setter without a ready pair
     assert pk.resolve_ready_pair([None, None]) is None and pk.resolve_ready_pair([]) is None
     assert pk.resolve_ready_pair([pk.ReadyPair(3, float("nan"), 8)]) is None       # no usable scale
+
+
+def test_guess_rank_bounds_the_miss_probability():
+    """The guessed start takes the r-th best distance of a 3968-row sample as a query's starting
+    threshold; r must make a too-tight guess rarer than guess_miss_ppm (Poisson tail) without admitting more rows than
+    the candidate lists survive."""
+    from scipy.stats import poisson
+
+    L = pk.lib()
+    S = 3968
+    for rows, k, want in ((10_000_000, 100, 3), (1_000_000, 100, 5), (100_000, 100, None), (70_000, 10, None), (5_000_000, 1, None)):
+        r = L.pkv_guess_rank(k, S, rows, 100)
+        x = k * S / rows
+        assert r >= 2 and poisson.sf(r - 1, x) <= 1e-4, (rows, k, r)
+        assert r == 2 or poisson.sf(r - 2, x) > 1e-4, "not the smallest such rank"
+        assert r * rows / S <= 16000
+        if want is not None:
+            assert r == want
+    assert L.pkv_guess_rank(100, S, 1_000_000, 1000) < L.pkv_guess_rank(100, S, 1_000_000, 1)      # looser is safer
+    assert L.pkv_guess_rank(100, S, 40_000_000, 100) == 0      # even the 2nd best of the sample admits too many rows
+    assert L.pkv_guess_rank(0, S, 1000, 100) == 0 and L.pkv_guess_rank(10, 0, 1000, 100) == 0
