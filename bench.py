@@ -498,7 +498,9 @@ class Workload:
         sub = min(a.batch, 1024)
         img_passes = -(-a.batch // 1024) * ((1 if sub <= 128 or kind in (3, 8) else -(-sub // 256)) if kind in (3, 4, 6, 7, 8) else -(-sub // 8))
         groups = min(-(-sub // 256), 4) if (kind in (3, 8) and sub > 128) else 1
-        share = {1: 1.002, 2: 1.06, 3: 1.25, 4: 1.44}[groups]
+        # (4 groups: 1.44 on the round-1 chunked schedule, 2.30 in the round-2 live launch, where the groups drift apart:
+        # profiles/r02_ncu_i8_b1024_live.txt, dram__bytes_read 17.75 GB for 7.72 GB of codes)
+        share = {1: 1.002, 2: 1.06, 3: 1.25, 4: 2.30}[groups]
         rescored = (c1.rescored_pairs - c0.rescored_pairs + c1.deferred_pairs - c0.deferred_pairs) / steps
         traffic = img_passes * alg_bytes * share + rescored * stored_row_bytes
         roof = {
