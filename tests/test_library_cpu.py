@@ -178,3 +178,30 @@ def test_guess_rank_bounds_the_miss_probability():
     assert L.pkv_guess_rank(100, S, 1_000_000, 1000) < L.pkv_guess_rank(100, S, 1_000_000, 1)      # looser is safer
     assert L.pkv_guess_rank(100, S, 40_000_000, 100) == 0      # even the 2nd best of the sample admits too many rows
     assert L.pkv_guess_rank(0, S, 1000, 100) == 0 and L.pkv_guess_rank(10, 0, 1000, 100) == 0
+
+
+def test_rust_ffi_binding_is_generated_from_the_header_and_complete():
+    """include/pkv_ffi.rs is the `extern "C"` block the Rust server adds: generated from pkv.h
+    (fresh), one `pub fn` per exported entry point, and #[repr(C)] structs whose fields are those of the ctypes
+    structures the GPU tests drive the library with (same names, same order, same sizes)."""
+    import ctypes as C
+    import subprocess
+    import sys
+
+    rc = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py"), "--check"]).returncode
+    assert rc == 0, "include/pkv_ffi.rs is stale: run tools/gen_rust_ffi.py"
+    rs = open(os.path.join(ROOT, "include", "pkv_ffi.rs")).read()
+    fns = set(re.findall(r"pub fn ([a-z0-9_]+)\(", rs))
+    assert fns == set(N.SIGNATURES) | {"sqlite3_pkv_init"}, fns ^ (set(N.SIGNATURES) | {"sqlite3_pkv_init"})
+    size = {"i8": 1, "u8": 1, "i32": 4, "u32": 4, "c_int": 4, "f32": 4, "i64": 8, "u64": 8, "f64": 8, "usize": 8}
+    pairs = {"PkvIndexInfo": N.IndexInfo, "PkvSearchParams": N.SearchParams, "PkvCounters": N.Counters,
+             "PkvRankParams": N.RankParams, "PkvCorpusInfo": N.CorpusInfo, "PkvSimilarParams": N.SimilarParams,
+             "PkvReadyPair": N.ReadyPair}
+    for rname, ct in pairs.items():
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % rname, rs, flags=re.S).group(1)
+        fields = re.findall(r"pub ([a-z0-9_]+): ([^,]+),", body)
+        assert [f for f, _ in fields] == [f[0] for f in ct._fields_], rname
+        for (fname, rtype), cf in zip(fields, ct._fields_):
+            want = C.sizeof(cf[1])
+            got = 8 if rtype.startswith("*") else size[rtype]
+            assert got == want, (rname, fname, rtype)
