@@ -78,3 +78,20 @@ def test_round2_default_line_carries_the_targets_and_the_measured_peak():
     assert c3["roofline"]["tensor_frac_of_nominal"] >= 0.40          # north_star: >= 40 % of the int8 tensor-pipe peak
     ref = _line("r02_final_reference.json")
     assert ref["config"] == j["config"], "both arms must describe the same configuration"
+
+
+def test_round2_eight_gpu_line_holds_configs_4_and_5_and_an_eight_rank_parity_leg():
+    """BASELINE configs 4 and 5 on 8 GPUs and N = 8 parity, as part of the line
+    `bench.py --gpus 8` prints under torchrun (the driver's own scaling run takes the same path)."""
+    j = _line("r02_final_multi_default_n8.json")
+    one = _line("r02_final_default.json")
+    assert j["n_gpus"] == 8 and j["scaling"] == "strong" and j["value"] > one["value"]
+    assert j["config"]["parallelism"] == "row-shard x8" and j["e2e"]["value"] > 0 and j["sustained"]["value"] > 0
+    p = j["parity"]
+    assert p["checked"].startswith("8 ranks x") and p["within_1e-5"] and p["counts_equal"] and p["ids_equal_frac"] == 1.0
+    c4, c5 = j["configs"]["C4"], j["configs"]["C5"]
+    assert c4["workload"].startswith("50Mx512 f16 cosine") and "batch=4096" in c4["workload"] and c4["n_gpus"] == 8
+    assert c4["value"] > 0 and c4["e2e"] > 0
+    assert "tag bitmap" in c5["workload"] and c5["n_gpus"] == 8 and c5["value"] > 0
+    two = _line("r02_final_multi_default_n2.json")
+    assert two["n_gpus"] == 2 and one["value"] < two["value"] < j["value"]

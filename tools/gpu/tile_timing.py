@@ -49,9 +49,11 @@ print("wait tmem_full by CTA rank:", [f"{x:.0f}" for x in per_rank])
 fl = t2[:, 2:18, :]
 print(f"loop top (thresholds, row figures, bound): {np.mean(epi[:,:,6][ok]/n):.0f} clk/tile, > 1500 clk in {100*np.mean(epi[:,:,7][ok]/n):.2f} % of tiles")
 nf = fl[:, :, 1][ok]
-print(f"flush_held: {nf.mean():.1f} calls per warp, {np.sum(fl[:,:,0][ok])/max(nf.sum(),1):.0f} clk per call, slowest {fl[:,:,2][ok].max():.0f}; "
+if nf.sum() > 0:
+  print(f"flush_held: {nf.mean():.1f} calls per warp, {np.sum(fl[:,:,0][ok])/max(nf.sum(),1):.0f} clk per call, slowest {fl[:,:,2][ok].max():.0f}; "
       f"{np.mean(fl[:,:,0][ok]/n):.0f} clk/tile")
 f3 = t3[:, 2:18, :]
 tot = max(nf.sum(), 1)
-print(f"  inside a flush: round (smem, ring) {np.sum(fl[:,:,3][ok])/tot:.0f}  park_complete {np.sum(f3[:,:,0][ok])/tot:.0f}  atomic issue {np.sum(f3[:,:,1][ok])/tot:.0f} clk")
+if nf.sum() > 0:
+  print(f"  inside a flush: round (smem, ring) {np.sum(fl[:,:,3][ok])/tot:.0f}  park_complete {np.sum(f3[:,:,0][ok])/tot:.0f}  atomic issue {np.sum(f3[:,:,1][ok])/tot:.0f} clk")
 ix.close()
