@@ -870,22 +870,51 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         uint32_t buf = 0, bph = 0;
         uint32_t hold_n = 0;  // entries in this warp's hold list (warp-uniform; img8_epi = 1)
         ParkPending pp{0u, 0u, 0, -1};
+#ifdef PKV_TILE_TIMING
+        long long te_wait = 0, te_ld = 0, te_proc = 0, te_n = 0, te_max = 0, te_slow = 0, te_pre = 0, te_pre_slow = 0;
+        long long te_flush = 0, te_nflush = 0, te_fmax = 0, tf_round = 0, tf_park = 0, tf_atom = 0, te_prev = 0;
+#endif
         // Flushes the first 32 held entries (one lane-parallel round: a second round would have to wait for the atomics
         // the first one has just issued) and moves the rest to the front of the list; `all`: the end of the scan.
         auto flush_held = [&](bool all) {
+#ifdef PKV_TILE_TIMING
+            const long long tf = clock64();
+#endif
             __syncwarp();
             for (uint32_t base = 0; base < hold_n; base += 32) {
+#ifdef PKV_TILE_TIMING
+                const long long f0 = clock64();
+#endif
                 const HeldOut h = flush_round<METRIC>(a, im, qbase, sh, ew, lane, base, hold_n < base + 32 ? hold_n : base + 32);
+#ifdef PKV_TILE_TIMING
+                const long long f1 = clock64();
+#endif
                 park_complete(im, pp);
+#ifdef PKV_TILE_TIMING
+                const long long f2 = clock64();
+#endif
                 if (h.q >= 0) {
                     pp.slot = atomicAdd(im.dlist.cnt + h.q, 1u);  // issued now, consumed at the next flush
                     pp.row = h.row;
                     pp.d = h.d;
                     pp.q = h.q;
                 }
+#ifdef PKV_TILE_TIMING
+                tf_round += f1 - f0;
+                tf_park += f2 - f1;
+                tf_atom += clock64() - f2;
+#endif
                 if (!all) break;
             }
             __syncwarp();
+#ifdef PKV_TILE_TIMING
+            if (!all) {
+                const long long dtf = clock64() - tf;
+                te_flush += dtf;
+                ++te_nflush;
+                if (dtf > te_fmax) te_fmax = dtf;
+            }
+#endif
             if (!all && hold_n > 32) {
                 const uint32_t rest = hold_n - 32;
                 uint32_t r0 = 0, r2 = 0;
@@ -920,9 +949,7 @@ scan_img8_kernel(const __grid_constant__ CUtensorMap tmap_rows, const ScanArgs a
         float qs;
         query_consts<METRIC>(qm, thr0, qc, qs);
 #ifdef PKV_TILE_TIMING
-        long long te_wait = 0, te_ld = 0, te_proc = 0, te_n = 0, te_max = 0, te_slow = 0, te_pre = 0, te_pre_slow = 0, te_flush = 0, te_nflush = 0, te_fmax = 0;
-        long long tf_round = 0, tf_park = 0, tf_atom = 0;
-        long long te_prev = clock64();
+        te_prev = clock64();
 #endif
         for (uint32_t tile = seq; tile < ntiles; tile += nseq) {
 #ifdef PKV_TILE_TIMING
